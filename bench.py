@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- agent-steps/s of the batched environment step on B200 (one JSON line on rank 0).
+
+    python bench.py --gpus N --steps K --warmup W              # this repo (CUDA)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm: oracle port, all host threads
+
+A "step" is one Environment.step over every environment of the workload (one launch of the fused
+kernel).  Default workload = BASELINE.json configs[3], the one the north_star target is quoted on:
+64 UAVs x 64 targets, 65 536 environments per GPU, MAAC-G reward (neighbour mean, cooperative 0.3),
+random-policy actions resident in HBM.  Environments are independent, so N GPUs run N shards with no
+data-path collective ("scaling": "weak": 65 536 environments per GPU); the only exchange is the episode
+statistics all-reduce (<= 8 doubles), done once after the timed region.
+
+value     = env x n_uav x K / device time (CUDA events, max over ranks), inputs resident in HBM.
+e2e       = same metric through BatchedEnvironment.step_host (the C-ABI call with HOST buffers):
+            pinned host actions in, observations / 4 reward planes / covered counts out, every step.
+roofline  = algorithmic bytes per launch (124 n + 48 m + 4 per env-step) / mean launch time
+            against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+cpu_baseline = the CPU oracle (C port of the reference loop, oracle/) on a bounded sample, all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n_uav, m_targets, envs per GPU, method, description)
+    "swarm64": (64, 64, 65536, "MAAC-G", "configs[3]: 64 UAV x 64 targets, 65536 envs/GPU, MAAC-G reward, random policy"),
+    "swarm64_self": (64, 64, 65536, "MAAC", "configs[3] with MAAC (cooperative=0) reward"),
+    "default4096": (10, 10, 4096, "MAAC", "configs[1]: default 10x10 scenario, 4096 envs, random policy, step+reward"),
+    "default_pmi16384": (10, 10, 16384, "MAAC-R", "configs[2]: default 10x10, 16384 envs, MAAC-R PMI reward (H=128)"),
+    "swarm64_pmi": (64, 64, 16384, "MAAC-R", "64x64, 16384 envs, MAAC-R PMI reward (H=128)"),
+}
+EPISODE = 200  # src/main.py:128 --num_steps default
+
+
+def alg_bytes_per_env_step(n, m):
+    """fp64 x,y,h in+out, int32 last action in+out... = 124 n + 48 m + 4 bytes."""
+    return 124 * n + 48 * m + 4
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_pmi(torch, hidden=128):
+    from marl_uavs_targets_tracking_b200 import PMINetwork
+    torch.manual_seed(42)
+    pmi = PMINetwork(hidden_dim=hidden)
+    for bn in (pmi.bn_comm, pmi.bn_obs, pmi.bn_boundary_state, pmi.bn1):
+        bn.running_mean.normal_(0, 0.3)
+        bn.running_var.uniform_(0.5, 1.5)
+    return pmi.eval()
+
+
+def cpu_oracle_rate(n, m, method, budget_s, threads, seed=0):
+    """Time the CPU oracle (oracle/, C port of the reference's loops) on a bounded sample of the workload."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from gpu_util import oracle_params_from_config, oracle_pmi_from_module
+    from philox_ref import reset_reference
+    from marl_uavs_targets_tracking_b200 import default_config
+    from oracle import Oracle
+    cfg = default_config(method, n, m)
+    P = oracle_params_from_config(cfg, n, m)
+    mode = {"MAAC": 0, "MAAC-G": 1, "MAAC-R": 2}[method]
+    pmi = oracle_pmi_from_module(make_pmi(torch)) if method == "MAAC-R" else None
+    orc = Oracle()
+    E = max(threads * 4, 8)
+    st = reset_reference(seed, E, n, m, 12, 2000, 2000)
+    st = {k: np.ascontiguousarray(v) for k, v in st.items()}
+    rng = np.random.RandomState(seed)
+    acts = rng.randint(0, 12, size=(E, n)).astype(np.int32)
+    t0 = time.perf_counter()
+    orc.step_batch(P, mode, float(cfg["cooperative"]), pmi, st, acts, nthreads=threads, want_tracker=False)
+    one = max(time.perf_counter() - t0, 1e-4)
+    steps = int(max(3, min(2000, budget_s / one)))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        acts = rng.randint(0, 12, size=(E, n)).astype(np.int32)
+        orc.step_batch(P, mode, float(cfg["cooperative"]), pmi, st, acts, nthreads=threads, want_tracker=False)
+    dt = time.perf_counter() - t0
+    return E * n * steps / dt, "%d envs x %d steps of %dx%d %s, %d threads, %.1f s" % (E, steps, n, m, method, threads, dt), E, steps, dt
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port (the Python
+    reference itself cannot travel to the GPU box), all host threads, same metric / config / unit."""
+    if rank != 0:
+        return
+    n, m, E, method, desc = WORKLOADS[args.workload]
+    threads = os.cpu_count() or 1
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from gpu_util import oracle_params_from_config, oracle_pmi_from_module
+    from philox_ref import reset_reference
+    from marl_uavs_targets_tracking_b200 import default_config
+    from oracle import Oracle
+    cfg = default_config(method, n, m)
+    P = oracle_params_from_config(cfg, n, m)
+    mode = {"MAAC": 0, "MAAC-G": 1, "MAAC-R": 2}[method]
+    pmi = oracle_pmi_from_module(make_pmi(torch)) if method == "MAAC-R" else None
+    orc = Oracle()
+    # bounded sample: enough envs to keep every thread busy, sized so K+W steps end within ~2 minutes
+    Es = max(threads * 8, 16)
+    st = {k: np.ascontiguousarray(v) for k, v in reset_reference(0, Es, n, m, 12, 2000, 2000).items()}
+    rng = np.random.RandomState(0)
+    acts = rng.randint(0, 12, size=(Es, n)).astype(np.int32)
+    t0 = time.perf_counter()
+    orc.step_batch(P, mode, float(cfg["cooperative"]), pmi, st, acts, nthreads=threads, want_tracker=False)
+    one = max(time.perf_counter() - t0, 1e-5)
+    total = args.steps + args.warmup
+    while Es > threads and one * total > 120:
+        Es //= 2
+        one /= 2
+    st = {k: np.ascontiguousarray(v[:Es]) for k, v in st.items()}
+    for _ in range(args.warmup):
+        orc.step_batch(P, mode, float(cfg["cooperative"]), pmi, st, rng.randint(0, 12, size=(Es, n)).astype(np.int32),
+                       nthreads=threads, want_tracker=False)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.step_batch(P, mode, float(cfg["cooperative"]), pmi, st, rng.randint(0, 12, size=(Es, n)).astype(np.int32),
+                       nthreads=threads, want_tracker=False)
+    dt = time.perf_counter() - t0
+    value = Es * n * args.steps / dt
+    sample = "%d envs (sample of %d x %d GPUs) x %d steps of %dx%d %s" % (Es, E, args.gpus, args.steps, n, m, method)
+    out = {"impl": "reference", "metric": "agent-steps/s", "value": value, "unit": "agent-steps/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": args.workload, "description": desc, "n_uav": n, "m_targets": m,
+                      "envs_per_gpu": E, "method": method},
+           "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": threads, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0,
+           "note": "CPU oracle (C restatement of the reference's Python loops, pinned to the reference by tests/golden); "
+                   "the Python reference itself measured 3.7e3 agent-steps/s/core on this scenario (SURVEY.md section 6)"}
+    print(json.dumps(out), flush=True)
+
+
+def measure_workload(torch, dist, env_cls, args, name, rank, world, device, steps, warmup, with_e2e, e2e_steps):
+    from marl_uavs_targets_tracking_b200 import default_config
+    n, m, E, method, desc = WORKLOADS[name]
+    if args.envs_per_gpu and name == args.workload:
+        E = args.envs_per_gpu
+    cfg = default_config(method, n, m)
+    pmi = make_pmi(torch) if method == "MAAC-R" else None
+    env = env_cls(n, m, 2000, 2000, 12, n_envs=E, device=device, env_id_offset=rank * E, seed=42, num_steps=EPISODE)
+    env.reset(cfg)
+    # random-policy actions resident in HBM: a bank of NB pre-drawn [E,n] tensors, rebound per step (no copy)
+    NB = 8
+    bank = torch.empty((NB, E, n), dtype=torch.int32, device=device)
+    for b in range(NB):
+        env.bind_actions(bank[b])
+        env.random_actions(seed=4242, step=b)
+    torch.cuda.synchronize(device)
+
+    def one_step(i):
+        if i % EPISODE == 0 and i > 0:
+            env.reset(cfg)
+        env.bind_actions(bank[i % NB])
+        env.step_device(cfg, pmi)
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for i in range(warmup):
+        one_step(i)
+    barrier()
+    l0 = env.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(device.index)
+    sampler.start()
+    ev0.record(torch.cuda.current_stream(device))
+    for i in range(steps):
+        one_step(warmup + i)
+    ev1.record(torch.cuda.current_stream(device))
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = env.launch_count() - l0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    res = {"name": name, "desc": desc, "n": n, "m": m, "E": E, "method": method, "ms": ms, "steps": steps,
+           "launches": launches, "clocks": clocks, "value": E * world * n * steps / (ms * 1e-3)}
+
+    if with_e2e:
+        h_act = torch.empty((NB, E, n), dtype=torch.int32).pin_memory()
+        h_act.copy_(bank.cpu())
+        h_obs = torch.empty((E, n, 12), dtype=torch.float32).pin_memory()
+        h_rew = torch.empty((4, E, n), dtype=torch.float32).pin_memory()
+        h_cov = torch.empty((E,), dtype=torch.int32).pin_memory()
+        for i in range(2):
+            env.step_host(cfg, pmi, h_act[i % NB], h_obs, h_rew, h_cov, chunks=args.chunks)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            env.step_host(cfg, pmi, h_act[i % NB], h_obs, h_rew, h_cov, chunks=args.chunks)
+        torch.cuda.synchronize(device)
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        res["e2e"] = {"value": E * world * n * e2e_steps / dt, "unit": "agent-steps/s",
+                      "h2d_bytes_per_step": E * n * 4, "d2h_bytes_per_step": E * n * 12 * 4 + 4 * E * n * 4 + E * 4,
+                      "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3, "chunks": args.chunks,
+                      "api": "BatchedEnvironment.step_host -> uavsim_step_host (pinned host buffers)"}
+        res["checksum"] = float(h_rew[0].double().sum())
+    # the one collective of the path: episode statistics (<= 8 doubles), outside the timed region
+    from marl_uavs_targets_tracking_b200 import reduce_episode_stats
+    res["episode_stats"] = reduce_episode_stats(env.episode_stats(), device=device)
+    env.close()
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="swarm64", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs-per-gpu", type=int, default=0)
+    ap.add_argument("--chunks", type=int, default=8, help="env ranges the host-buffer step is pipelined over")
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU time spent on the cpu_baseline sample")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads and the CPU baseline")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from marl_uavs_targets_tracking_b200 import BatchedEnvironment
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
+
+    main_res = measure_workload(torch, dist, BatchedEnvironment, args, args.workload, rank, world, device, args.steps,
+                                args.warmup, True, args.e2e_steps)
+    extras = {}
+    if not args.no_extras:
+        for name in ("swarm64_self", "default4096", "default_pmi16384", "swarm64_pmi"):
+            if name == args.workload:
+                continue
+            r = measure_workload(torch, dist, BatchedEnvironment, args, name, rank, world, device,
+                                 min(args.steps, 100), 5, False, 0)
+            extras[name] = {"value": r["value"], "unit": "agent-steps/s", "ms_per_step": r["ms"] / r["steps"],
+                            "envs_per_gpu": r["E"], "n_uav": r["n"], "m_targets": r["m"], "method": r["method"],
+                            "roofline_frac": r["value"] / world * alg_bytes_per_env_step(r["n"], r["m"]) / r["n"] / (hbm_peak()[0] * 1e9)}
+
+    if rank == 0:
+        n, m, E = main_res["n"], main_res["m"], main_res["E"]
+        peak, peak_src = hbm_peak()
+        bytes_per_launch = E * alg_bytes_per_env_step(n, m)
+        # launches in the timed region = `steps` step kernels (+ a reset pair per episode boundary)
+        ms_per_step = main_res["ms"] / main_res["steps"]
+        achieved = bytes_per_launch / (ms_per_step * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(args.workload)
+            except Exception:
+                traffic = None
+        out = {"metric": "agent-steps/s", "value": main_res["value"], "unit": "agent-steps/s", "n_gpus": world,
+               "steps": main_res["steps"], "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": args.workload, "description": main_res["desc"], "n_uav": n, "m_targets": m,
+                          "envs_per_gpu": E, "method": main_res["method"], "episode_len": EPISODE,
+                          "l2": "per-step working set %.0f MB > 126 MB L2 (inputs larger than L2, no flush needed)" % (bytes_per_launch / 1e6)},
+               "clocks": main_res["clocks"], "e2e": main_res["e2e"], "gpu_launches": main_res["launches"],
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            "traffic": traffic, "peak_source": peak_src, "kernel": "uavsim_step_kernel",
+                            "bytes_per_launch": bytes_per_launch,
+                            "bytes_per_agent_step": alg_bytes_per_env_step(n, m) / n},
+               "episode_stats": main_res["episode_stats"], "other_workloads": extras}
+        if world == 1 and not args.no_extras:
+            v, sample, _, _, _ = cpu_oracle_rate(n, m, main_res["method"], args.cpu_seconds, os.cpu_count() or 1)
+            out["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                   "sample": sample}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,94 @@
+"""PMI network: host-side mirror of the reference interface and BatchNorm folding.
+
+`PMINetwork` has the reference's constructor, parameter names (`state_dict()` keys) and
+`forward` / `inference` semantics (src/models/PMINet.py:20-72), so checkpoints written by the
+reference's `PMINetwork.save` load here and vice versa.  Training (`train_pmi`,
+src/models/PMINet.py:74-100) is learner-side code and stays stock PyTorch in the reference;
+it is out of scope for this path.
+
+`fold_pmi` turns any module / state dict with those names into the BN-folded fp32 arrays the
+CUDA path consumes (include/uavsim.h: UavSimPmiWeights).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+BN_EPS = 1e-5  # torch.nn.BatchNorm1d default, used by the reference unchanged
+_BRANCHES = (("fc_comm", "bn_comm", 5), ("fc_obs", "bn_obs", 4), ("fc_boundary_state", "bn_boundary_state", 3))
+
+
+class PMINetwork(nn.Module):
+    """12-d -> scalar MLP: three branch Linear+BN+ReLU over the communication (5), observation (4)
+    and boundary/state (3) slices, concatenated, Linear+BN+ReLU, Linear (src/models/PMINet.py:29-62)."""
+
+    def __init__(self, comm_dim=5, obs_dim=4, boundary_state_dim=3, hidden_dim=64, b2_size=3000):
+        super().__init__()
+        self.comm_dim, self.obs_dim, self.boundary_state_dim = comm_dim, obs_dim, boundary_state_dim
+        self.hidden_dim, self.b2_size = hidden_dim, b2_size
+        self.fc_comm = nn.Linear(comm_dim, hidden_dim)
+        self.bn_comm = nn.BatchNorm1d(hidden_dim)
+        self.fc_obs = nn.Linear(obs_dim, hidden_dim)
+        self.bn_obs = nn.BatchNorm1d(hidden_dim)
+        self.fc_boundary_state = nn.Linear(boundary_state_dim, hidden_dim)
+        self.bn_boundary_state = nn.BatchNorm1d(hidden_dim)
+        self.fc1 = nn.Linear(hidden_dim * 3, hidden_dim)
+        self.bn1 = nn.BatchNorm1d(hidden_dim)
+        self.fc2 = nn.Linear(hidden_dim, 1)
+
+    def forward(self, x):
+        if isinstance(x, np.ndarray):
+            x = torch.tensor(x, dtype=torch.float32)
+        x = x.float()
+        a, b = self.comm_dim, self.comm_dim + self.obs_dim
+        parts = (torch.relu(self.bn_comm(self.fc_comm(x[:, :a]))),
+                 torch.relu(self.bn_obs(self.fc_obs(x[:, a:b]))),
+                 torch.relu(self.bn_boundary_state(self.fc_boundary_state(x[:, b:b + self.boundary_state_dim]))))
+        return self.fc2(torch.relu(self.bn1(self.fc1(torch.cat(parts, dim=1)))))
+
+    def inference(self, single_data):
+        self.eval()
+        if isinstance(single_data, np.ndarray):
+            single_data = torch.tensor(single_data, dtype=torch.float32)
+        if single_data.ndim == 1:
+            single_data = single_data.unsqueeze(0)
+        with torch.no_grad():
+            return self.forward(single_data).item()
+
+
+def _as_state(pmi):
+    sd = pmi.state_dict() if hasattr(pmi, "state_dict") else pmi
+    out = {}
+    for k, v in sd.items():
+        out[k] = v.detach().cpu().double().numpy() if torch.is_tensor(v) else np.asarray(v, dtype=np.float64)
+    return out
+
+
+def fold_pmi(pmi):
+    """Fold eval-mode BatchNorm (running statistics) into the preceding Linear layers.
+
+    y = (W x + b - mean) / sqrt(var + eps) * gamma + beta  ==  (s*W) x + ((b - mean)*s + beta),
+    s = gamma / sqrt(var + eps).  Folding is done in float64, the result rounded to float32.
+    Returns dict(hidden, w0 [3H,5], b0 [3H], w1 [H,3H], b1 [H], w2 [H], b2 float).
+    """
+    sd = _as_state(pmi)
+    H = sd["fc1.weight"].shape[0]
+    w0 = np.zeros((3 * H, 5), np.float64)
+    b0 = np.zeros(3 * H, np.float64)
+    for b, (fc, bn, dim) in enumerate(_BRANCHES):
+        s = sd[bn + ".weight"] / np.sqrt(sd[bn + ".running_var"] + BN_EPS)
+        w0[b * H:(b + 1) * H, :dim] = sd[fc + ".weight"] * s[:, None]
+        b0[b * H:(b + 1) * H] = (sd[fc + ".bias"] - sd[bn + ".running_mean"]) * s + sd[bn + ".bias"]
+    s1 = sd["bn1.weight"] / np.sqrt(sd["bn1.running_var"] + BN_EPS)
+    w1 = sd["fc1.weight"] * s1[:, None]
+    b1 = (sd["fc1.bias"] - sd["bn1.running_mean"]) * s1 + sd["bn1.bias"]
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)  # noqa: E731
+    return {"hidden": int(H), "w0": f32(w0), "b0": f32(b0), "w1": f32(w1), "b1": f32(b1),
+            "w2": f32(sd["fc2.weight"].reshape(-1)), "b2": float(np.float32(sd["fc2.bias"].reshape(-1)[0]))}
+
+
+def pmi_version(pmi):
+    """Cheap change detector: sum of the in-place version counters of all parameters and buffers
+    (optimizer steps, load_state_dict and BN running-stat updates all bump them)."""
+    if not hasattr(pmi, "state_dict"):
+        return id(pmi)
+    return (id(pmi), sum(int(v._version) for v in pmi.state_dict(keep_vars=True).values()))

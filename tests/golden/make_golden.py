@@ -16,6 +16,7 @@ old/new) communication mask is the one the reference actually used.
 usage:  python tests/golden/make_golden.py [--ref /root/reference/src]
 """
 import argparse
+import json
 import os
 import random
 import sys
@@ -139,6 +140,7 @@ def run_case(name, out_dir, mods, cfg, mode, T, seed, actions=None, init_overrid
         cfg["uav"]["dc"], cfg["uav"]["dp"], cfg["target"]["v_max"], pi / float(cfg["target"]["h_max"]),
         cfg["uav"]["alpha"], cfg["uav"]["beta"], cfg["uav"]["gamma"], cfg["cooperative"]], dtype=np.float64)
     save["params_i"] = np.array([n, m, env_c["na"], T, seed, {"self": 0, "mean": 1, "pmi": 2}[mode]], dtype=np.int64)
+    save["config_json"] = np.array(json.dumps(cfg))  # the exact dict handed to reset()/step()
     if pmi is not None:
         for k, v in pmi.state_dict().items():
             save["pmi." + k] = v.detach().cpu().numpy()

@@ -1,0 +1,301 @@
+"""GPU parity: the CUDA path (through the C ABI) against the golden vectors recorded from the
+reference and against the CPU oracle on seeded batches.
+
+Bars (BASELINE.json north_star): integer / index outputs bit-exact -- the five range masks, the
+covered count, per-target tracker counts, the done flag; float state and rewards within 1e-5.
+Tolerance rule: |got - ref| <= TOL * max(|ref|, 1) for observations and rewards (they cross zero),
+true relative error for positions.  TOL = 1e-5 is the contract; the observed error is ~1e-7 (outputs
+are stored as fp32) and the tests also assert a tighter 2e-6 so regressions are caught early.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden
+from gpu_util import (MASKS, golden_config, golden_pmi_module, max_scaled_err, oracle_params_from_config,
+                      oracle_pmi_from_module)
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5         # contract
+TOL_TIGHT = 2e-6   # what fp32 outputs of an fp64 computation should achieve
+TOL_PMI = 1e-5     # MAAC-R reward (fp32 MLP, different summation order)
+
+
+def _env(n, m, cfg, E, **kw):
+    from marl_uavs_targets_tracking_b200 import BatchedEnvironment
+    e = cfg["environment"]
+    return BatchedEnvironment(n, m, e["x_max"], e["y_max"], e["na"], n_envs=E, device="cuda:0", **kw)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_cuda_matches_reference_golden(name):
+    """Replayed reset + recorded actions, E=3 identical environments (so one CTA holds several)."""
+    g = load_golden(name)
+    cfg = golden_config(g)
+    n, m, T = int(g["params_i"][0]), int(g["params_i"][1]), int(g["params_i"][3])
+    mode = int(g["params_i"][5])
+    pmi = golden_pmi_module(g)
+    E = 3
+    env = _env(n, m, cfg, E, record_masks=True, track_counts=True, num_steps=T)
+    rep = lambda a: np.broadcast_to(np.asarray(a), (E,) + np.asarray(a).shape).copy()  # noqa: E731
+    env.set_state(cfg, *(rep(g[k + "0"]) for k in ("ux", "uy", "uh", "ua", "tx", "ty", "th")))
+    obs0 = env.get_states().double().cpu().numpy()
+    assert max_scaled_err(obs0[0], g["obs0"]) <= TOL_TIGHT
+    worst = {}
+    for t in range(T):
+        a = torch.as_tensor(rep(g["actions"][t]), device="cuda:0")
+        obs, rew, cov = env.step(cfg, pmi, a)
+        st = {k: v.cpu().numpy() for k, v in env.get_state().items()}
+        for e in range(E):
+            # integer outputs: bit-exact
+            for k in MASKS:
+                assert np.array_equal(env.masks[k][e].cpu().numpy().astype(bool), g[k][t]), (name, t, k, e)
+            assert int(cov[e]) == int(g["covered"][t]), (name, t, "covered")
+            assert np.array_equal(env.tracker_counts[e].cpu().numpy(), g["cover_mask"][t].sum(0)), (name, t, "tracker")
+            assert np.array_equal(st["ua"][e], g["actions"][t])
+            assert int(env.done[e]) == int(t + 1 == T)
+        for k in ("ux", "uy", "uh", "tx", "ty", "th"):
+            err = float(np.max(np.abs(st[k][0] - g[k][t]) / np.maximum(np.abs(g[k][t]), 1e-300)))
+            if k in ("uh", "th"):  # headings cross zero: scale by max(|ref|, 1)
+                err = max_scaled_err(st[k][0], g[k][t])
+            worst[k] = max(worst.get(k, 0.0), err)
+            assert np.array_equal(st[k][0], st[k][E - 1])  # replicas agree bit for bit
+        o = obs.double().cpu().numpy()
+        worst["obs"] = max(worst.get("obs", 0.0), max_scaled_err(o[0], g["obs"][t]))
+        for key, gk in (("rewards", "rewards"), ("target_tracking_reward", "tt"), ("boundary_punishment", "bp"),
+                        ("duplicate_tracking_punishment", "dup")):
+            r = rew[key].double().cpu().numpy()
+            worst[gk] = max(worst.get(gk, 0.0), max_scaled_err(r[0], g[gk][t]))
+            assert np.array_equal(r[0], r[E - 1])
+    print(name, {k: "%.1e" % v for k, v in worst.items()})
+    for k in ("ux", "uy", "uh", "tx", "ty", "th"):
+        assert worst[k] <= 1e-9, (k, worst[k])       # fp64 state: far inside the 1e-5 bar
+    for k in ("obs", "tt", "bp", "dup"):
+        assert worst[k] <= TOL_TIGHT, (k, worst[k])
+    assert worst["rewards"] <= (TOL_PMI if mode == 2 else TOL_TIGHT), worst["rewards"]
+    env.close()
+
+
+@pytest.mark.parametrize("n,m,method,E,T", [(10, 10, "MAAC", 256, 200), (10, 10, "MAAC-G", 256, 200),
+                                             (10, 10, "MAAC-R", 128, 200), (64, 64, "MAAC-G", 64, 200),
+                                             (64, 64, "MAAC-R", 16, 60), (64, 64, "MAAC", 64, 60),
+                                             (128, 40, "MAAC-G", 5, 30), (3, 200, "MAAC-R", 7, 30)])
+def test_cuda_matches_oracle_on_seeded_batches(oracle, n, m, method, E, T):
+    """Philox reset + Philox random policy on the GPU; the oracle replays the same state and actions."""
+    from marl_uavs_targets_tracking_b200 import PMINetwork, default_config
+    cfg = default_config(method, n, m)
+    coop = float(cfg["cooperative"])
+    pmi = None
+    if method == "MAAC-R":
+        torch.manual_seed(1)
+        pmi = PMINetwork(hidden_dim=128)
+        for bn in (pmi.bn_comm, pmi.bn_obs, pmi.bn_boundary_state, pmi.bn1):
+            bn.running_mean.normal_(0, 0.3)
+            bn.running_var.uniform_(0.5, 1.5)
+        pmi.eval()
+    env = _env(n, m, cfg, E, track_counts=True, seed=123)
+    env.reset(cfg)
+    P = oracle_params_from_config(cfg, n, m)
+    opmi = oracle_pmi_from_module(pmi) if pmi is not None else None
+    omode = {"MAAC": 0, "MAAC-G": 1, "MAAC-R": 2}[method]
+    st = {k: np.ascontiguousarray(v.cpu().numpy()) for k, v in env.get_state().items()}
+    worst = {"obs": 0.0, "rew": 0.0, "terms": 0.0, "pos": 0.0}
+    for t in range(T):
+        acts = env.random_actions(seed=99, step=t)
+        a_host = acts.cpu().numpy().copy()
+        assert a_host.min() >= 0 and a_host.max() < cfg["environment"]["na"]
+        obs, rew4, cov = env.step_device(cfg, pmi)
+        ref = oracle.step_batch(P, omode, coop, opmi, st, a_host, nthreads=8)
+        assert np.array_equal(cov.cpu().numpy(), ref["covered"]), (t, "covered")
+        assert np.array_equal(env.tracker_counts.cpu().numpy(), ref["tracker_cnt"]), (t, "tracker")
+        worst["obs"] = max(worst["obs"], max_scaled_err(obs.double().cpu().numpy(), ref["obs"]))
+        r = rew4.double().cpu().numpy()
+        worst["rew"] = max(worst["rew"], max_scaled_err(r[0], ref["rew4"][0]))
+        worst["terms"] = max(worst["terms"], max_scaled_err(r[1:], ref["rew4"][1:]))
+        for k in ("ux", "uy", "tx", "ty"):
+            worst["pos"] = max(worst["pos"], float(np.max(np.abs(env.get_state()[k].cpu().numpy() - st[k]) / np.maximum(np.abs(st[k]), 1.0))))
+    print(n, m, method, {k: "%.1e" % v for k, v in worst.items()})
+    assert worst["pos"] <= 1e-9
+    assert worst["obs"] <= TOL_TIGHT and worst["terms"] <= TOL_TIGHT
+    assert worst["rew"] <= (TOL_PMI if method == "MAAC-R" else TOL_TIGHT)
+    # episode statistics accumulated on the device == sums of the per-step outputs (only last step checked here)
+    env.close()
+
+
+def test_reset_and_random_policy_match_philox_reference():
+    from marl_uavs_targets_tracking_b200 import default_config
+    from philox_ref import actions_reference, reset_reference
+    cfg = default_config("MAAC", 10, 7)
+    env = _env(10, 7, cfg, 33, env_id_offset=1000, seed=5)
+    env.reset(cfg, seed=5)
+    ep_seed = (5 * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    ref = reset_reference(ep_seed, 33, 10, 7, 12, 2000, 2000, env_id_offset=1000)
+    st = env.get_state()
+    for k in ("ux", "uy", "uh", "tx", "ty", "th", "ua"):
+        assert np.array_equal(st[k].cpu().numpy(), ref[k]), k
+    assert st["uh"].abs().max() <= np.pi and st["tx"].min() >= 0 and st["tx"].max() < 2000
+    a = env.random_actions(seed=77, step=12).cpu().numpy()
+    assert np.array_equal(a, actions_reference(77, 12, 33, 10, 12, env_id_offset=1000))
+    # pre-step observation: -1 blocks + (x/dc, y/dc, a/Na)  (src/agent/uav.py:170-190)
+    o = env.get_states().cpu().numpy()
+    assert np.all(o[..., :9] == -1)
+    np.testing.assert_allclose(o[..., 9], ref["ux"] / 500, rtol=1e-6)
+    np.testing.assert_allclose(o[..., 11], ref["ua"] / 12, rtol=1e-6)
+    env.close()
+
+
+def test_sharding_is_invisible_in_the_results():
+    """Global env ids key the RNG: 2 shards of 8 == 1 handle of 16, bit for bit."""
+    from marl_uavs_targets_tracking_b200 import default_config, shard_envs
+    cfg = default_config("MAAC-G", 10, 10)
+    full = _env(10, 10, cfg, 16, seed=3)
+    full.reset(cfg)
+    shards = []
+    for r in range(2):
+        cnt, off = shard_envs(16, r, 2)
+        s = _env(10, 10, cfg, cnt, env_id_offset=off, seed=3)
+        s.reset(cfg)
+        shards.append(s)
+    for t in range(25):
+        full.random_actions(11, t); full.step_device(cfg, None)
+        for s in shards:
+            s.random_actions(11, t); s.step_device(cfg, None)
+    for k in ("ux", "uy", "uh", "tx", "ty", "th", "ua"):
+        cat = torch.cat([s.get_state()[k] for s in shards])
+        assert torch.equal(cat, full.get_state()[k]), k
+    assert torch.equal(torch.cat([s._rew4 for s in shards], dim=1), full._rew4)
+    assert torch.equal(torch.cat([s._obs for s in shards]), full._obs)
+    sf = full.episode_stats()
+    ss = [s.episode_stats() for s in shards]
+    assert sf["env_steps"] == 16 * 25 == sum(s["env_steps"] for s in ss)
+    assert sf["covered_sum"] == sum(s["covered_sum"] for s in ss)
+    assert sf["covered_max"] == max(s["covered_max"] for s in ss)
+    assert abs(sf["rewards"] - sum(s["rewards"] for s in ss)) < 1e-9
+    for e in [full] + shards:
+        e.close()
+
+
+@pytest.mark.parametrize("method", ["MAAC-G", "MAAC-R"])
+def test_host_buffer_step_equals_device_step(method):
+    from marl_uavs_targets_tracking_b200 import PMINetwork, default_config
+    cfg = default_config(method, 10, 10)
+    torch.manual_seed(0)
+    pmi = PMINetwork(hidden_dim=64).eval() if method == "MAAC-R" else None
+    E = 1000
+    a_env, b_env = _env(10, 10, cfg, E, seed=8), _env(10, 10, cfg, E, seed=8)
+    a_env.reset(cfg); b_env.reset(cfg)
+    h_act = torch.empty((E, 10), dtype=torch.int32).pin_memory()
+    h_obs = torch.empty((E, 10, 12), dtype=torch.float32).pin_memory()
+    h_rew = torch.empty((4, E, 10), dtype=torch.float32).pin_memory()
+    h_cov = torch.empty((E,), dtype=torch.int32).pin_memory()
+    for t in range(12):
+        acts = a_env.random_actions(4, t)
+        h_act.copy_(acts.cpu())
+        a_env.step_device(cfg, pmi)
+        b_env.step_host(cfg, pmi, h_act, h_obs, h_rew, h_cov, chunks=1 + t % 5)
+        assert torch.equal(h_obs, a_env._obs.cpu()) and torch.equal(h_rew, a_env._rew4.cpu())
+        assert torch.equal(h_cov, a_env._covered.cpu())
+    a_env.close(); b_env.close()
+
+
+def test_episode_stats_equal_output_sums():
+    from marl_uavs_targets_tracking_b200 import default_config
+    cfg = default_config("MAAC-G", 10, 10)
+    env = _env(10, 10, cfg, 777, seed=2)
+    env.reset(cfg)
+    acc = np.zeros(4)
+    cs, cm = 0, 0
+    for t in range(20):
+        env.random_actions(1, t)
+        _, rew4, cov = env.step_device(cfg, None)
+        acc += rew4.double().sum(dim=(1, 2)).cpu().numpy()
+        cs += int(cov.sum()); cm = max(cm, int(cov.max()))
+    s = env.episode_stats()
+    got = np.array([s["rewards"], s["target_tracking_reward"], s["boundary_punishment"], s["duplicate_tracking_punishment"]])
+    np.testing.assert_allclose(got, acc, rtol=1e-6, atol=1e-3)  # outputs are fp32, the accumulators fp64
+    assert s["covered_sum"] == cs and s["covered_max"] == cm and s["env_steps"] == 777 * 20
+    env.reset(cfg)
+    assert env.episode_stats()["env_steps"] == 0
+    env.close()
+
+
+def test_reference_shaped_api_single_env():
+    """n_envs == 1: the call pattern of src/train.py:160-192 (operate_epoch) works unchanged."""
+    from marl_uavs_targets_tracking_b200 import Environment, default_config
+    cfg = default_config("MAAC-G")
+    e = cfg["environment"]
+    env = Environment(n_uav=e["n_uav"], m_targets=e["m_targets"], x_max=e["x_max"], y_max=e["y_max"], na=e["na"])
+    env.reset(config=cfg)
+    rng = np.random.RandomState(0)
+    ep_ret, covered_list = 0.0, []
+    for i in range(15):
+        cfg["step"] = i + 1
+        action_list = []
+        for uav in env.uav_list:
+            state = uav.get_local_state()
+            assert isinstance(state, np.ndarray) and state.shape == (12,) and state.dtype == np.float64
+            action_list.append(int(rng.randint(0, 12)))
+        next_state_list, reward_list, covered = env.step(cfg, None, action_list)
+        assert isinstance(next_state_list, list) and len(next_state_list) == 10 and next_state_list[0].shape == (12,)
+        assert set(reward_list) == {"rewards", "target_tracking_reward", "boundary_punishment", "duplicate_tracking_punishment"}
+        assert all(isinstance(v, list) and len(v) == 10 for v in reward_list.values())
+        assert isinstance(covered, int)
+        ep_ret += sum(reward_list["rewards"])
+        covered_list.append(covered)
+        np.testing.assert_array_equal(next_state_list[3], env.uav_list[3].get_local_state())
+    assert len(env.position["all_uav_xs"]) == 15 and len(env.position["all_uav_xs"][0]) == 10
+    assert env.covered_target_num == covered_list
+    assert env.uav_list[0].dp == 200 and isinstance(env.uav_list[0].x, float)
+    env.close()
+
+
+@pytest.mark.parametrize("n,m,E,method", [(10, 10, 4096, "MAAC"), (64, 64, 65536, "MAAC-G"), (10, 10, 16384, "MAAC-R")])
+def test_full_size_properties(n, m, E, method):
+    """BASELINE.json sizes, size-independent properties: the second half of the batch is a copy of the
+    first half (same state, same actions) and must produce bit-identical results wherever it lands;
+    covered == #targets with a tracker; rewards in [-1,1]; terms in their normalised ranges."""
+    from marl_uavs_targets_tracking_b200 import PMINetwork, default_config
+    cfg = default_config(method, n, m)
+    torch.manual_seed(3)
+    pmi = PMINetwork(hidden_dim=128).eval() if method == "MAAC-R" else None
+    env = _env(n, m, cfg, E, track_counts=True, seed=17)
+    env.reset(cfg)
+    half = E // 2
+    st = env.get_state()
+    for k, v in st.items():
+        v[half:] = v[:half]
+    env.set_state(cfg, *(st[k] for k in ("ux", "uy", "uh", "ua", "tx", "ty", "th")))
+    for t in range(10):
+        a = env.random_actions(5, t)
+        a[half:] = a[:half]
+        obs, rew4, cov = env.step_device(cfg, pmi)
+        assert torch.equal(obs[:half], obs[half:]) and torch.equal(rew4[:, :half], rew4[:, half:])
+        assert torch.equal(cov[:half], cov[half:])
+        assert torch.equal(cov, (env.tracker_counts > 0).sum(dim=1).to(torch.int32))
+        assert float(rew4[0].min()) >= -1 and float(rew4[0].max()) <= 1
+        assert float(rew4[1].min()) >= 0 and float(rew4[1].max()) <= 1
+        assert float(rew4[2].min()) >= -1 and float(rew4[2].max()) <= 0
+        assert float(rew4[3].min()) >= -1 and float(rew4[3].max()) <= 0
+        assert torch.isfinite(obs).all()
+    for k, v in env.get_state().items():
+        assert torch.equal(v[:half], v[half:]), k
+    env.close()
+
+
+def test_errors_are_loud():
+    from marl_uavs_targets_tracking_b200 import BatchedEnvironment, UavSimError, default_config
+    cfg = default_config("MAAC-R", 10, 10)
+    with pytest.raises(UavSimError):
+        BatchedEnvironment(129, 10, 2000, 2000, 12, n_envs=2).reset(default_config("MAAC", 129, 10))
+    env = _env(10, 10, cfg, 4)
+    with pytest.raises(UavSimError):
+        env.step_device(cfg, None)  # step before reset
+    env.reset(cfg)
+
+    class NotAPmi:
+        def state_dict(self):
+            return {}
+    with pytest.raises(Exception):
+        env.step_device(cfg, NotAPmi())
+    env.close()

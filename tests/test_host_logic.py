@@ -1,0 +1,101 @@
+"""Host-side logic that needs no GPU: BN folding, config mapping, env sharding, the gloo stats reduce."""
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import load_golden
+from marl_uavs_targets_tracking_b200 import (PMINetwork, default_config, episode_summary, fold_pmi, params_from_config,
+                                             reduce_episode_stats, shard_envs)
+
+
+def _folded_forward(f, x):
+    """numpy fp32 evaluation of the folded network, the arithmetic the CUDA path performs."""
+    H = f["hidden"]
+    h0 = np.zeros((x.shape[0], 3 * H), np.float32)
+    for b, (off, dim) in enumerate(((0, 5), (5, 4), (9, 3))):
+        h0[:, b * H:(b + 1) * H] = x[:, off:off + dim] @ f["w0"][b * H:(b + 1) * H, :dim].T
+    h0 = np.maximum(h0 + f["b0"], 0)
+    h1 = np.maximum(h0 @ f["w1"].T + f["b1"], 0)
+    return h1 @ f["w2"] + np.float32(f["b2"])
+
+
+def test_bn_folding_matches_eval_forward():
+    torch.manual_seed(0)
+    for H in (32, 64, 128):
+        net = PMINetwork(hidden_dim=H)
+        for bn in (net.bn_comm, net.bn_obs, net.bn_boundary_state, net.bn1):
+            bn.running_mean.normal_(0, 0.3)
+            bn.running_var.uniform_(0.5, 1.5)
+            bn.weight.data.normal_(1, 0.2)
+            bn.bias.data.normal_(0, 0.1)
+        net.eval()
+        x = torch.randn(257, 12)
+        with torch.no_grad():
+            ref = net(x).squeeze(1).numpy()
+        got = _folded_forward(fold_pmi(net), x.numpy())
+        np.testing.assert_allclose(got, ref, rtol=0, atol=2e-6)
+        f = fold_pmi(net)
+        assert np.all(f["w0"][H:2 * H, 4:] == 0) and np.all(f["w0"][2 * H:, 3:] == 0)  # padding stays zero
+
+
+def test_pmi_mirror_loads_reference_state_dict_names():
+    g = load_golden("d10_pmi_s42")
+    sd = {k[4:]: torch.tensor(g[k]) for k in g.files if k.startswith("pmi.")}
+    net = PMINetwork(hidden_dim=128)
+    net.load_state_dict(sd)  # strict: same keys and shapes as the reference's PMINetwork
+    net.eval()
+    assert isinstance(net.inference(np.zeros(12)), float)
+    assert fold_pmi(sd)["hidden"] == 128
+
+
+def test_params_from_config_converts_like_the_reference():
+    p = params_from_config(default_config("MAAC-G"), 10, 10, 2000, 2000, 12, 200)
+    assert (p.n_uav, p.m_targets, p.na, p.num_steps) == (10, 10, 12, 200)
+    assert p.uav_h_max == np.pi / 6.0 and p.tgt_h_max == np.pi / 6.0  # src/environment.py:98,100
+    assert (p.dc, p.dp, p.dt, p.uav_v_max, p.tgt_v_max) == (500, 200, 1, 20, 5)
+    assert default_config("MAAC")["cooperative"] == 0  # src/main.py:75-76
+
+
+def test_shard_envs_partitions_exactly():
+    for total in (1, 7, 4096, 65536):
+        for world in (1, 2, 3, 8):
+            parts = [shard_envs(total, r, world) for r in range(world)]
+            assert sum(c for c, _ in parts) == total
+            assert all(parts[r][1] + parts[r][0] == (parts[r + 1][1] if r + 1 < world else total) for r in range(world))
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    local = {"rewards": 1.5 + rank, "target_tracking_reward": 2.0 * (rank + 1), "boundary_punishment": -0.25,
+             "duplicate_tracking_punishment": -1.0 * rank, "covered_sum": 10.0 + rank, "covered_max": 3.0 + 2 * rank,
+             "env_steps": 100.0}
+    red = reduce_episode_stats(local, device="cpu")
+    q.put((rank, red))
+    dist.destroy_process_group()
+
+
+def test_stats_reduce_world_size_2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = dict(q.get(timeout=120) for _ in range(2))
+    [p.join(60) for p in procs]
+    assert res[0] == res[1]
+    r = res[0]
+    assert r["rewards"] == 4.0 and r["target_tracking_reward"] == 6.0 and r["boundary_punishment"] == -0.5
+    assert r["duplicate_tracking_punishment"] == -1.0 and r["covered_sum"] == 21.0 and r["covered_max"] == 5.0
+    assert r["env_steps"] == 200.0
+    s = episode_summary(r, n_uav=10)
+    assert s["return"] == 4.0 / 2000 and s["average_covered_targets"] == 21.0 / 200 and s["max_covered_targets"] == 5.0
+
+
+def test_reduce_is_identity_without_process_group():
+    st = {"rewards": 1.0, "target_tracking_reward": 2.0, "boundary_punishment": 3.0, "duplicate_tracking_punishment": 4.0,
+          "covered_sum": 5.0, "covered_max": 6.0, "env_steps": 7.0}
+    assert reduce_episode_stats(st) == st
