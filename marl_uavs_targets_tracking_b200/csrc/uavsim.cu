@@ -786,8 +786,13 @@ extern "C" int uavsim_create(const UavSimParams *p, int64_t n_envs, int64_t env_
     free(h);
     return UAVSIM_ERR_UNSUPPORTED;
   }
-  CUDA_TRY(cudaFuncSetAttribute(uavsim_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_step));
-  CUDA_TRY(cudaFuncSetAttribute(uavsim_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_step));
+  // the attribute is per function, not per handle: only ever raise it (several handles may coexist)
+  static size_t s_step_attr[64] = {0};
+  if (h->smem_step > s_step_attr[device & 63]) {
+    CUDA_TRY(cudaFuncSetAttribute(uavsim_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_step));
+    CUDA_TRY(cudaFuncSetAttribute(uavsim_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_step));
+    s_step_attr[device & 63] = h->smem_step;
+  }
   int occ = 1;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, uavsim_step_kernel<false>, NT, h->smem_step));
   if (occ < 1) occ = 1;
@@ -932,7 +937,11 @@ template <int CPT, int TM>
 static int pmi_launch_t(uavsim_t *h, int64_t e0, int64_t cnt, double coop, cudaStream_t st, bool configure_only) {
   auto kern = uavsim_pmi_kernel<CPT, TM>;
   if (configure_only) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_pmi));
+    static size_t s_attr[64] = {0};  // per template instance and device: only ever raise it
+    if (h->smem_pmi > s_attr[h->device & 63]) {
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_pmi));
+      s_attr[h->device & 63] = h->smem_pmi;
+    }
     int occ = 1;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PMI_NT, h->smem_pmi));
     if (occ < 1) occ = 1;
