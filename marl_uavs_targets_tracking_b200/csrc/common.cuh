@@ -1,0 +1,141 @@
+// common.cuh -- parameter blocks, the handle, and small device helpers shared by the kernels of libuavsim.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/uavsim.h"
+#include "philox.cuh"
+
+#define NT 256       // threads per CTA, step kernel (one thread per UAV, NT/n environments per CTA)
+#define PMI_NT 256   // threads per CTA, PMI kernel
+#define STAT_W 8     // doubles per statistics slot
+
+static thread_local char g_err[512] = "";
+#define SET_ERR(...) snprintf(g_err, sizeof(g_err), __VA_ARGS__)
+#define CUDA_TRY(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      SET_ERR("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return (int)_e;                                                                      \
+    }                                                                                      \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// kernel-side parameter block
+// ------------------------------------------------------------------------------------------------
+struct KParams {
+  int n, m, na, num_steps;
+  int64_t E;                  // environments of this handle (plane stride of rew4 is E*n)
+  int64_t env_id_offset;      // global id of env 0 (RNG key only)
+  double x_max, y_max;
+  double dtv_u, dtv_t;        // dt*v_max of UAVs / targets (Python evaluates dt*v_max first)
+  double dc, dp, two_dp;      // two_dp = radio*dp, radio = 2 (src/agent/uav.py:214)
+  double tv, uv;              // target / uav v_max
+  double s_dp_le, s_dp_lt, s_dc_le, s_2dp_le;  // exact squared thresholds
+  double alpha, beta, gamma;
+  double tt_hi;               // 2*m_targets            (src/environment.py:207-208)
+  double dup_lo;              // -e/2*n_uav             (src/environment.py:209-210)
+};
+
+struct PmiDev {
+  int H;
+  const float *w0, *b0, *w1t, *b1, *w2;  // w1t = fc1 weight transposed to [3H,H]
+  float b2;
+};
+
+typedef void (*StepKernelFn)(const KParams, const UavSimBuffers, const double *, int64_t, int64_t, int, int, double,
+                             int, double *);
+
+struct uavsim {
+  UavSimParams hp;
+  KParams kp;
+  UavSimBuffers buf;
+  bool bound;
+  int device, sm_count;
+  int64_t E;
+  double *d_dth;      // [3*na] dt * heading-rate per action (src/agent/uav.py:73-81,96), its cos and sin
+  double *d_stats;    // [2][slots][STAT_W] per-CTA partial sums (step kernel | pmi kernel)
+  double *d_stats8;   // [8] reduced
+  double *h_stats8;   // pinned
+  int stat_slots;
+  int epb, grid_max;
+  StepKernelFn step_fn[2];  // [MASKS]
+  size_t smem_step;
+  // pmi
+  bool has_pmi;
+  PmiDev pmi;
+  float *d_pmi_blob;
+  int pmi_g, pmi_pmax, pmi_tm, pmi_grid_max;
+  size_t smem_pmi;
+  // host-buffer pipeline
+  cudaStream_t s_in, s_comp, s_out;
+  cudaEvent_t ev_user, ev_in[16], ev_comp[16];
+  int64_t t, launches;
+};
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+#define PI_D 3.141592653589793
+
+// Python float `%` with a positive divisor (CPython float_rem): fmod, then shift negatives up.
+__device__ __forceinline__ double pymod_pos(double a, double b) {
+  double r = fmod(a, b);
+  if (r < 0.0) r += b;
+  return r;
+}
+
+// src/utils/data_util.py:43-56 clip_and_normalize, choice 0 with floor 0
+__device__ __forceinline__ double clipnorm_0(double v, double hi) {
+  v = fmin(fmax(v, 0.0), hi);
+  return (v - 0.0) / (hi - 0.0);
+}
+// choice -1 with ceil 0: (v-floor)/(0-floor) - 1
+__device__ __forceinline__ double clipnorm_m1(double v, double lo) {
+  v = fmin(fmax(v, lo), 0.0);
+  return (v - lo) / (0.0 - lo) - 1.0;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_max(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_down_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide reduction of per-thread statistics into this CTA's slot (accumulating across launches;
+// one writer per slot, no atomics, so the totals are reproducible for a fixed launch geometry).
+__device__ void block_stats_commit(double *red /*smem [nwarps*6]*/, double *slot, double v0, double v1, double v2,
+                                   double v3, double v4, int vmax, double v6, int nthreads) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = nthreads >> 5;
+  v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3); v4 = warp_sum(v4);
+  v6 = warp_sum(v6);
+  vmax = warp_max(vmax);
+  __syncthreads();
+  if (lane == 0) {
+    red[wid * 7 + 0] = v0; red[wid * 7 + 1] = v1; red[wid * 7 + 2] = v2; red[wid * 7 + 3] = v3;
+    red[wid * 7 + 4] = v4; red[wid * 7 + 5] = (double)vmax; red[wid * 7 + 6] = v6;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int w = 0; w < nw; w++) {
+      for (int k = 0; k < 5; k++) a[k] += red[w * 7 + k];
+      a[5] = fmax(a[5], red[w * 7 + 5]);
+      a[6] += red[w * 7 + 6];
+    }
+    for (int k = 0; k < 5; k++) slot[k] += a[k];
+    slot[5] = fmax(slot[5], a[5]);
+    slot[6] += a[6];
+  }
+}
+
