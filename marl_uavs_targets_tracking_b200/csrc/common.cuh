@@ -40,6 +40,9 @@ struct KParams {
   double alpha, beta, gamma;
   double tt_hi;               // 2*m_targets            (src/environment.py:207-208)
   double dup_lo;              // -e/2*n_uav             (src/environment.py:209-210)
+  // fp32 prefilter: map centre, validity radius, guarded squared thresholds (thr^2 + fp32 error bound)
+  double cx, cy, rmax;
+  float f_dp, f_dc, f_2dp, f_dcmv;  // f_dcmv: dc + dt*v_max (old position bounded through the new one)
 };
 
 struct PmiDev {

@@ -2,59 +2,103 @@
 //
 // CTA = epb environments, thread q = (env q / n, UAV q % n), epb * n <= NT.  Per step:
 //   phase 0  targets move and reflect (src/agent/target.py:27-60), UAVs integrate their heading-rate action
-//            (src/agent/uav.py:73-99); old and new UAV records are staged in shared memory as double2 pairs
-//            so the pair loops read them with broadcast 128-bit loads.
-//   phase 1  one thread per UAV walks all targets and all other UAVs: range tests on exact squared fp64
-//            thresholds, branch-free accumulation of the observation sums, tracking / duplicate terms,
-//            neighbour bit set, per-target tracker counts; boundary term; normalisation and weights.
+//            (src/agent/uav.py:73-99); old and new UAV records are staged in shared memory (one block per
+//            environment, double2 records read with broadcast 128-bit loads, plus fp32 shadows of the
+//            positions relative to the map centre).
+//   phase 1  one thread per UAV, partners in chunks of 32.  (A) an fp32 prefilter walks every partner of the
+//            chunk (4 flops + compares) and keeps a candidate bit when the fp32 squared distance is below the
+//            threshold PLUS a guard band that bounds the fp32 error; (B) only the candidates are re-evaluated
+//            in fp64 on the exact squared thresholds, which decide every mask; hits accumulate the observation
+//            sums, tracking / duplicate terms, neighbour bits and per-target tracker counts.  Then the boundary
+//            term, normalisation and weights.
 //   phase 2  cooperative reward (self / neighbour mean; PMI is finished by uavsim_pmi_kernel), coverage
 //            count, coalesced output stores, per-CTA episode statistics.
 //
 // Precision plan.  Everything that decides an integer output (the five range masks, coverage) is fp64 in
-// the reference's evaluation order.  The observation sums are fp64 but LINEAR: mean_j((x_j - x_i)/dc) is
-// accumulated as sum(x_j - x_i) and scaled once -- valid because the reference's per-row weight
-// min(||(rx,ry) - (x,y)||, 1) (src/agent/uav.py:162-186) is exactly 1 unless |x| < 2 and |y| < 2; UAVs
-// inside that 4 m x 4 m corner take the exact per-row path (`EXACTW`).  The transcendental parts of the
-// tracking and duplicate terms (sqrt, exp on hits) are evaluated in fp32: they only feed fp32 outputs
-// that are normalised by 2m and e/2*n (error <= ~2e-7 against the 1e-5 bar).
+// the reference's evaluation order; the fp32 prefilter is only ever conservative (KParams::f_*, see
+// prefilter_threshold in uavsim.cu) and is bypassed for an environment whose entities left the radius the
+// error bound assumes.  The observation sums are fp64 but LINEAR: mean_j((x_j - x_i)/dc) is accumulated as
+// sum(x_j - x_i) and scaled once -- valid because the reference's per-row weight min(||(rx,ry) - (x,y)||, 1)
+// (src/agent/uav.py:162-186) is exactly 1 unless |x| < 2 and |y| < 2; UAVs inside that 4 m x 4 m corner
+// take the exact per-row path (agent_exact).  The transcendental parts of the tracking and duplicate terms
+// (sqrt, exp on hits) are evaluated in fp32: they only feed fp32 outputs that are normalised by 2m and
+// e/2*n (error <= ~1e-7 against the 1e-5 bar).
 #pragma once
 #include "common.cuh"
 
-struct StepSmem {
-  double2 *tpos, *tvel;          // [epb*m] moved targets: (x, y), (cos h, sin h) * tv / uv
-  double2 *npos, *nhd;           // [epb*n] UAV after the move: (x, y), (cos h, sin h)
-  double2 *opos, *ohd;           // [epb*n] UAV before the move
-  double *raw;                   // [epb*n]
-  double *dth;                   // [3*na] per action: dt*rate, cos(dt*rate), sin(dt*rate)
-  double *red;                   // [64]
-  float *obs;                    // [epb*n*12]
-  int *oa, *na_;                 // [epb*n] previous / new action index
-  int *tcnt;                     // [epb*m] UAVs strictly within dp of each target
+// ------------------------------------------------------------------------------------------------
+// shared memory: one block per environment (byte offsets below), then CTA-wide arrays
+// ------------------------------------------------------------------------------------------------
+struct EnvLayout {
+  int tpos, tvel, npos, nhd, opos, ohd, tposf, nposf, na_, oa, stride;
+};
+
+__host__ __device__ constexpr EnvLayout env_layout(int n, int m) {
+  EnvLayout L{};
+  int o = 0;
+  L.tpos = o; o += 16 * m;   // double2 (x, y) after the move
+  L.tvel = o; o += 16 * m;   // double2 (cos h, sin h) * tv / uv
+  L.npos = o; o += 16 * n;   // double2 UAV (x, y) after the move
+  L.nhd = o; o += 16 * n;    // double2 (cos h, sin h) after the move
+  L.opos = o; o += 16 * n;   // before the move
+  L.ohd = o; o += 16 * n;
+  L.tposf = o; o += 8 * m;   // float2 target position relative to the map centre
+  L.nposf = o; o += 8 * n;   // float2 new UAV position relative to the map centre
+  L.na_ = o; o += 4 * n;     // new action index
+  L.oa = o; o += 4 * n;      // previous action index
+  L.stride = (o + 15) & ~15;
+  return L;
+}
+
+struct CtaSmem {
+  unsigned char *env;  // [epb] environment blocks
+  double *raw;         // [epb*n]
+  double *dth;         // [3*na] per action: dt*rate, cos(dt*rate), sin(dt*rate)
+  double *red;         // [64]
+  float *obs;          // [epb*n*12]
+  int *tcnt;           // [epb*m] UAVs strictly within dp of each target
+  int *far;            // [epb] 1 if an entity is farther than KParams::rmax from the map centre
 };
 
 static size_t step_smem_bytes(int n, int m, int na, int epb) {
-  size_t d = (size_t)epb * m * 4 + (size_t)epb * n * 9 + (size_t)3 * na + 64;
-  size_t f = (size_t)epb * n * 12;
-  size_t i = (size_t)epb * n * 2 + (size_t)epb * m;
-  return d * 8 + 32 + f * 4 + i * 4;
+  const EnvLayout L = env_layout(n, m);
+  size_t b = (size_t)epb * L.stride;
+  b += ((size_t)epb * n + 3 * (size_t)na + 64) * 8 + 8;
+  b += (size_t)epb * n * 12 * 4;
+  b += ((size_t)epb * m + (size_t)epb) * 4;
+  return b + 16;
 }
 
-__device__ __forceinline__ StepSmem carve(unsigned char *base, int n, int m, int na, int epb) {
-  StepSmem s;
-  double2 *d2 = reinterpret_cast<double2 *>(base);  // base is 16-byte aligned
-  const size_t em = (size_t)epb * m, en = (size_t)epb * n;
-  s.tpos = d2; d2 += em; s.tvel = d2; d2 += em;
-  s.npos = d2; d2 += en; s.nhd = d2; d2 += en; s.opos = d2; d2 += en; s.ohd = d2; d2 += en;
-  double *d = reinterpret_cast<double *>(d2);
-  s.raw = d; d += en;
+__device__ __forceinline__ CtaSmem carve(unsigned char *base, int n, int m, int na, int epb, int stride) {
+  CtaSmem s;
+  s.env = base;
+  double *d = reinterpret_cast<double *>(base + (size_t)epb * stride);  // stride is a multiple of 16
+  s.raw = d; d += (size_t)epb * n;
   s.dth = d; d += 3 * na;
   s.red = d; d += 64;
-  d += (en + 3 * (size_t)na) & 1;  // keep obs 16-byte aligned with plain pointer arithmetic (stays a shared pointer)
+  d += ((size_t)epb * n + 3 * (size_t)na) & 1;  // keep obs 16-byte aligned (plain pointer arithmetic: stays shared)
   s.obs = reinterpret_cast<float *>(d);
-  int *ip = reinterpret_cast<int *>(s.obs + en * 12);
-  s.oa = ip; ip += en; s.na_ = ip; ip += en; s.tcnt = ip;
+  int *ip = reinterpret_cast<int *>(s.obs + (size_t)epb * n * 12);
+  s.tcnt = ip; ip += (size_t)epb * m;
+  s.far = ip;
   return s;
 }
+
+// typed views into one environment block
+struct EnvView {
+  unsigned char *b;
+  EnvLayout L;
+  __device__ __forceinline__ double2 *tpos() const { return reinterpret_cast<double2 *>(b + L.tpos); }
+  __device__ __forceinline__ double2 *tvel() const { return reinterpret_cast<double2 *>(b + L.tvel); }
+  __device__ __forceinline__ double2 *npos() const { return reinterpret_cast<double2 *>(b + L.npos); }
+  __device__ __forceinline__ double2 *nhd() const { return reinterpret_cast<double2 *>(b + L.nhd); }
+  __device__ __forceinline__ double2 *opos() const { return reinterpret_cast<double2 *>(b + L.opos); }
+  __device__ __forceinline__ double2 *ohd() const { return reinterpret_cast<double2 *>(b + L.ohd); }
+  __device__ __forceinline__ float2 *tposf() const { return reinterpret_cast<float2 *>(b + L.tposf); }
+  __device__ __forceinline__ float2 *nposf() const { return reinterpret_cast<float2 *>(b + L.nposf); }
+  __device__ __forceinline__ int *na_() const { return reinterpret_cast<int *>(b + L.na_); }
+  __device__ __forceinline__ int *oa() const { return reinterpret_cast<int *>(b + L.oa); }
+};
 
 // what phase 1 produces for one UAV
 struct AgentOut {
@@ -79,11 +123,13 @@ __device__ __forceinline__ float fast_ex2f(float x) {
 // Taken by UAVs within 2 m of the origin in both coordinates (never inlined: it is cold).
 // ------------------------------------------------------------------------------------------------
 template <bool MASKS>
-__device__ __noinline__ void agent_exact(const KParams &P, const UavSimBuffers &B, double xi, double yi, double chi,
-                                         double shi, int ai, int i, int n, int m, const double2 *tpos,
-                                         const double2 *tvel, const double2 *npos, const double2 *nhd,
-                                         const double2 *opos, const double2 *ohd, const int *na_, const int *oa,
-                                         int *tcnt, float *ob, int64_t mrow_t, int64_t mrow_u, AgentOut &O) {
+__device__ __noinline__ void agent_exact(const KParams &P, const UavSimBuffers &B, const EnvView V, int *tcnt, int i,
+                                         int n, int m, float *ob, int64_t mrow_t, int64_t mrow_u, AgentOut *Op) {
+  const double2 me = V.npos()[i], mh = V.nhd()[i];
+  const double xi = me.x, yi = me.y, chi = mh.x, shi = mh.y;
+  const int ai = V.na_()[i];
+  const double2 *tpos = V.tpos(), *tvel = V.tvel(), *npos = V.npos(), *nhd = V.nhd(), *opos = V.opos(), *ohd = V.ohd();
+  const int *na_ = V.na_(), *oa = V.oa();
   double tt = 0, o0 = 0, o1 = 0, o2 = 0, o3 = 0;
   int nobs = 0;
   for (int t = 0; t < m; t++) {
@@ -146,14 +192,12 @@ __device__ __noinline__ void agent_exact(const KParams &P, const UavSimBuffers &
   } else {
     ob[5] = ob[6] = ob[7] = ob[8] = -1.f;
   }
-  O.tt = tt; O.dup = dup;
-  O.nb[0] = nb[0]; O.nb[1] = nb[1]; O.nb[2] = nb[2]; O.nb[3] = nb[3];
+  Op->tt = tt; Op->dup = dup;
+  Op->nb[0] = nb[0]; Op->nb[1] = nb[1]; Op->nb[2] = nb[2]; Op->nb[3] = nb[3];
 }
 
 // ------------------------------------------------------------------------------------------------
-// fast path: same masks, linear sums, fp32 transcendentals.
-// CN / CM: compile-time n_uav / m_targets (0 = run-time).  WARP_ENV: every warp lies inside one
-// environment (n % 32 == 0), so "j already moved" (j < i) is warp-uniform outside the warp's own 32 UAVs.
+// fast path
 // ------------------------------------------------------------------------------------------------
 struct CommAcc {
   double sx, sy, sc, ss;
@@ -162,114 +206,198 @@ struct CommAcc {
 
 enum { PAIR_MOVED = 0, PAIR_MIXED = 1, PAIR_UNMOVED = 2 };
 
+__device__ __forceinline__ uint32_t low_bits(int len) { return len >= 32 ? 0xffffffffu : ((1u << len) - 1u); }
+
+// (A) fp32 prefilter over one chunk of partner positions: up to three candidate masks for three guarded
+// thresholds t0 <= t1 <= t2 (unused ones are compiled out).  FULL: the chunk has exactly 32 entries
+// (compile-time bits, fully unrolled).
+template <bool FULL, bool W0, bool W1, bool W2>
+__device__ __forceinline__ void prefilter(const float2 *__restrict__ pf, int len, float xf, float yf, float t0, float t1,
+                                          float t2, uint32_t &m0, uint32_t &m1, uint32_t &m2) {
+  m0 = m1 = m2 = 0;
+  if (FULL) {
+#pragma unroll
+    for (int jj = 0; jj < 32; jj++) {
+      const float2 p = pf[jj];
+      const float dx = p.x - xf, dy = p.y - yf;
+      const float d2 = fmaf(dx, dx, dy * dy);
+      if (W0) m0 |= (d2 <= t0) ? (1u << jj) : 0u;
+      if (W1) m1 |= (d2 <= t1) ? (1u << jj) : 0u;
+      if (W2) m2 |= (d2 <= t2) ? (1u << jj) : 0u;
+    }
+  } else {
+    for (int jj = 0; jj < len; jj++) {
+      const float2 p = pf[jj];
+      const float dx = p.x - xf, dy = p.y - yf;
+      const float d2 = fmaf(dx, dx, dy * dy);
+      if (W0) m0 |= (d2 <= t0) ? (1u << jj) : 0u;
+      if (W1) m1 |= (d2 <= t1) ? (1u << jj) : 0u;
+      if (W2) m2 |= (d2 <= t2) ? (1u << jj) : 0u;
+    }
+  }
+}
+
 // One chunk of up to 32 partner UAVs j = jb .. jb+len-1 for UAV i.
-//   PAIR_MOVED    every j moved before i (j < i): one distance serves the reward tests and communication
+//   PAIR_MOVED    every j moved before i (j < i): its new state serves the reward tests and communication
 //   PAIR_UNMOVED  every j moves after i: new-new distance for the rewards, new-old for communication
 //   PAIR_MIXED    per-lane order (j in the same warp as i, or a run-time sized environment)
-template <int KIND, bool MASKS>
-__device__ __forceinline__ uint32_t pair_chunk(const KParams &P, const UavSimBuffers &B, int jb, int len, int i,
-                                               double xi, double yi, const double2 *__restrict__ npos,
-                                               const double2 *__restrict__ nhd, const double2 *__restrict__ opos,
-                                               const double2 *__restrict__ ohd, const int *__restrict__ na_,
-                                               const int *__restrict__ oa, float k_ex0, float k_ex1, CommAcc &A,
-                                               float &dupA, float &dupB, int64_t mrow_u) {
-  uint32_t bits = 0, bit = 1;
-  auto body = [&](int j, float &dupacc) {
-    const double2 np = npos[j];
-    const double dxn = np.x - xi, dyn = np.y - yi;
-    const double d2n = dxn * dxn + dyn * dyn;
-    const bool valid = (KIND != PAIR_MIXED) || (j != i);
-    const bool hd = valid && (d2n <= P.s_2dp_le);  // uav.py:225
-    const bool hn = valid && (d2n <= P.s_dp_le);   // uav.py:305
-    // exp((2dp - d)/(2dp)) = 2^(log2e - d*log2e/(2dp))
-    const float v = fast_ex2f(fmaf(fast_sqrtf((float)d2n), k_ex1, k_ex0));
-    dupacc += hd ? v : 0.f;
-    if (hn) bits |= bit;
-    bit += bit;
-    bool hc;
-    if (KIND == PAIR_MOVED) {
-      hc = d2n <= P.s_dc_le;  // uav.py:135, partner already at its new state
-      if (hc) { const double2 h = nhd[j]; A.sx += dxn; A.sy += dyn; A.sc += h.x; A.ss += h.y; A.sa += na_[j]; A.cnt++; }
-    } else {
+// Candidates: `cn` = evaluate j's NEW position exactly (needed up to dc if j moved first, else up to 2dp);
+// `co` = evaluate j's OLD position exactly (j moves later, communication range dc).  The old position is
+// within dt*v of the new one, so co is prefiltered on the NEW position with the threshold dc + dt*v.
+// Returns the neighbour bits (d <= dp) of the chunk.
+template <int KIND, bool FULL, bool MASKS>
+__device__ __forceinline__ uint32_t pair_chunk(const KParams &P, const UavSimBuffers &B, const EnvView V, int jb, int len,
+                                               int i, double xi, double yi, float xf, float yf, bool far_env,
+                                               float k_ex0, float k_ex1, CommAcc &A, double &dup, int64_t mrow_u) {
+  uint32_t cn, co;
+  if (far_env) {
+    cn = low_bits(len);
+    co = cn;
+  } else {
+    uint32_t m_2dp, m_dc, m_dcmv;
+    prefilter<FULL, KIND != PAIR_MOVED, KIND != PAIR_UNMOVED, KIND != PAIR_MOVED>(V.nposf() + jb, len, xf, yf, P.f_2dp,
+                                                                                 P.f_dc, P.f_dcmv, m_2dp, m_dc, m_dcmv);
+    if (KIND == PAIR_MOVED) { cn = m_dc; co = 0; }
+    else if (KIND == PAIR_UNMOVED) { cn = m_2dp; co = m_dcmv; }
+    else {
+      const int sj = i - jb;  // bits below sj moved before i, bits above move after
+      const uint32_t lt = sj <= 0 ? 0u : low_bits(sj);
+      cn = (m_dc & lt) | (m_2dp & ~lt);
+      co = m_dcmv;
+    }
+  }
+  if (KIND == PAIR_MOVED) co = 0;
+  if (KIND == PAIR_MIXED) {
+    const int sj = i - jb;
+    const uint32_t lt = sj <= 0 ? 0u : low_bits(sj);
+    const uint32_t self = (sj >= 0 && sj < 32) ? (1u << sj) : 0u;
+    cn &= ~self;
+    co &= ~(lt | self);
+  }
+  if (MASKS)
+    for (int jj = 0; jj < len; jj++) { B.comm_mask[mrow_u + jb + jj] = 0; B.nbr_mask[mrow_u + jb + jj] = 0; B.dup_mask[mrow_u + jb + jj] = 0; }
+
+  // ---- (B) exact fp64 evaluation of the candidates, ascending j like the reference's loops
+  const double2 *npos = V.npos(), *nhd = V.nhd(), *opos = V.opos(), *ohd = V.ohd();
+  uint32_t todo = cn | co, nbits = 0;
+  while (todo) {
+    const int jj = __ffs((int)todo) - 1;
+    const uint32_t bit = 1u << jj;
+    todo &= todo - 1;
+    const int j = jb + jj;
+    bool hc = false;
+    if (cn & bit) {
+      const double2 np = npos[j];
+      const double dxn = np.x - xi, dyn = np.y - yi;
+      const double d2n = dxn * dxn + dyn * dyn;
+      const bool hd = d2n <= P.s_2dp_le;  // uav.py:225
+      const bool hn = d2n <= P.s_dp_le;   // uav.py:305
+      if (hd) dup += (double)fast_ex2f(fmaf(fast_sqrtf((float)d2n), k_ex1, k_ex0));  // exp((2dp - d)/(2dp))
+      if (hn) nbits |= bit;
+      if (MASKS) { B.nbr_mask[mrow_u + j] = hn; B.dup_mask[mrow_u + j] = hd; }
+      const bool moved = (KIND == PAIR_MOVED) || (KIND == PAIR_MIXED && j < i);
+      if (moved && d2n <= P.s_dc_le) {  // uav.py:135, partner already at its new state
+        const double2 h = nhd[j];
+        A.sx += dxn; A.sy += dyn; A.sc += h.x; A.ss += h.y; A.sa += V.na_()[j]; A.cnt++;
+        hc = true;
+      }
+    }
+    if (KIND != PAIR_MOVED && (co & bit)) {
       const double2 op = opos[j];
       const double dxo = op.x - xi, dyo = op.y - yi;
       const double d2o = dxo * dxo + dyo * dyo;
-      if (KIND == PAIR_UNMOVED) {
-        hc = d2o <= P.s_dc_le;  // partner still at its old state
-        if (hc) { const double2 h = ohd[j]; A.sx += dxo; A.sy += dyo; A.sc += h.x; A.ss += h.y; A.sa += oa[j]; A.cnt++; }
-      } else {
-        const bool hc_new = (j < i) && (d2n <= P.s_dc_le);
-        const bool hc_old = (j > i) && (d2o <= P.s_dc_le);
-        if (hc_new) { const double2 h = nhd[j]; A.sx += dxn; A.sy += dyn; A.sc += h.x; A.ss += h.y; A.sa += na_[j]; A.cnt++; }
-        if (hc_old) { const double2 h = ohd[j]; A.sx += dxo; A.sy += dyo; A.sc += h.x; A.ss += h.y; A.sa += oa[j]; A.cnt++; }
-        hc = hc_new || hc_old;
+      if (d2o <= P.s_dc_le) {  // partner still at its old state
+        const double2 h = ohd[j];
+        A.sx += dxo; A.sy += dyo; A.sc += h.x; A.ss += h.y; A.sa += V.oa()[j]; A.cnt++;
+        hc = true;
       }
     }
-    if (MASKS) { B.comm_mask[mrow_u + j] = hc; B.nbr_mask[mrow_u + j] = hn; B.dup_mask[mrow_u + j] = hd; }
-  };
-  int j = jb;
-  const int jend = jb + len;
-#pragma unroll 2
-  for (; j + 1 < jend; j += 2) { body(j, dupA); body(j + 1, dupB); }
-  if (j < jend) body(j, dupA);
-  return bits;
+    if (MASKS) B.comm_mask[mrow_u + j] = hc;
+  }
+  return nbits;
 }
 
 template <int CN, int CM, bool WARP_ENV, bool MASKS>
-__device__ __forceinline__ void agent_fast(const KParams &P, const UavSimBuffers &B, double xi, double yi, double chi,
-                                           double shi, int ai, int i, int n_rt, int m_rt,
-                                           const double2 *__restrict__ tpos, const double2 *__restrict__ tvel,
-                                           const double2 *__restrict__ npos, const double2 *__restrict__ nhd,
-                                           const double2 *__restrict__ opos, const double2 *__restrict__ ohd,
-                                           const int *__restrict__ na_, const int *__restrict__ oa, int *tcnt,
-                                           float *ob, int64_t mrow_t, int64_t mrow_u, AgentOut &O) {
+__device__ __forceinline__ void agent_fast(const KParams &P, const UavSimBuffers &B, const EnvView V, int *tcnt, int i,
+                                           int n_rt, int m_rt, bool far_env, float *ob, int64_t mrow_t, int64_t mrow_u,
+                                           AgentOut &O) {
   const int n = CN ? CN : n_rt, m = CM ? CM : m_rt;
-  const float inv_dp_f = (float)(1.0 / P.dp);
-  const float k_ex0 = 1.4426950408889634f, k_ex1 = (float)(-1.4426950408889634 / P.two_dp);
+  const double2 me = V.npos()[i], mh = V.nhd()[i];
+  const double xi = me.x, yi = me.y, chi = mh.x, shi = mh.y;
+  const float2 mef = V.nposf()[i];
+  const float xf = mef.x, yf = mef.y;
 
   // ---- targets: observe_target (uav.py:101-122), tracking reward (uav.py:199-212), coverage (environment.py:246-253)
-  double ox = 0, oy = 0, ovx = 0, ovy = 0;
-  float ttf = 0.f;
-  int nobs = 0;
-#pragma unroll 4
-  for (int t = 0; t < m; t++) {
-    const double2 tp = tpos[t];
-    const double dx = tp.x - xi, dy = tp.y - yi;
-    const double d2 = dx * dx + dy * dy;
-    const bool hit = d2 <= P.s_dp_le;
-    if (MASKS) { B.obs_mask[mrow_t + t] = hit; B.cover_mask[mrow_t + t] = (d2 <= P.s_dp_lt); }
-    if (hit) {
-      const double2 tv = tvel[t];
-      ox += dx; oy += dy; ovx += tv.x; ovy += tv.y;
-      nobs++;
-      ttf += 2.0f - fast_sqrtf((float)d2) * inv_dp_f;  // 1 + (dp - d)/dp
-      if (d2 <= P.s_dp_lt) atomicAdd(&tcnt[t], 1);
+  {
+    const float inv_dp_f = (float)(1.0 / P.dp);
+    double ox = 0, oy = 0, ovx = 0, ovy = 0, tt = 0;
+    int nobs = 0;
+    const double2 *tpos = V.tpos(), *tvel = V.tvel();
+    for (int tb = 0; tb < m; tb += 32) {
+      const int len = min(32, m - tb);
+      uint32_t ct, u1, u2;
+      if (far_env) ct = low_bits(len);
+      else if (CM && (CM % 32 == 0)) prefilter<true, true, false, false>(V.tposf() + tb, 32, xf, yf, P.f_dp, 0.f, 0.f, ct, u1, u2);
+      else prefilter<false, true, false, false>(V.tposf() + tb, len, xf, yf, P.f_dp, 0.f, 0.f, ct, u1, u2);
+      if (MASKS)
+        for (int jj = 0; jj < len; jj++) { B.obs_mask[mrow_t + tb + jj] = 0; B.cover_mask[mrow_t + tb + jj] = 0; }
+      while (ct) {
+        const int jj = __ffs((int)ct) - 1;
+        ct &= ct - 1;
+        const int t = tb + jj;
+        const double2 tp = tpos[t];
+        const double dx = tp.x - xi, dy = tp.y - yi;
+        const double d2 = dx * dx + dy * dy;
+        const bool hit = d2 <= P.s_dp_le;
+        if (MASKS) { B.obs_mask[mrow_t + t] = hit; B.cover_mask[mrow_t + t] = (d2 <= P.s_dp_lt); }
+        if (hit) {
+          const double2 tv = tvel[t];
+          ox += dx; oy += dy; ovx += tv.x; ovy += tv.y;
+          nobs++;
+          tt += (double)(2.0f - fast_sqrtf((float)d2) * inv_dp_f);  // 1 + (dp - d)/dp
+          if (d2 <= P.s_dp_lt) atomicAdd(&tcnt[t], 1);
+        }
+      }
     }
+    // observation part of the local state (uav.py:176-186; row weights are all 1 here), -1 block when empty
+    if (nobs) {
+      const double k = (double)nobs;
+      ob[5] = (float)(ox / P.dp / k);
+      ob[6] = (float)(oy / P.dp / k);
+      ob[7] = (float)((ovx - k * chi) / k);
+      ob[8] = (float)((ovy - k * shi) / k);
+    } else {
+      ob[5] = ob[6] = ob[7] = ob[8] = -1.f;
+    }
+    O.tt = tt;
   }
 
   // ---- UAVs: observe_uav in the sequential update order (uav.py:124-147, environment.py:133-138),
   //      duplicate-tracking punishment (uav.py:214-229), neighbour set (uav.py:305)
+  const float k_ex0 = 1.4426950408889634f, k_ex1 = (float)(-1.4426950408889634 / P.two_dp);
   CommAcc A = {0, 0, 0, 0, 0, 0};
-  float dupA = 0.f, dupB = 0.f;  // two partial sums keep the fp32 accumulation error ~1e-7 after normalisation
-  uint32_t nb[4] = {0, 0, 0, 0};
+  double dup = 0;
   const int w0 = i & ~31;  // first UAV of this warp (WARP_ENV)
 #pragma unroll
   for (int c = 0; c < 4; c++) {
     const int jb = 32 * c;
+    uint32_t nbits = 0;
     if (jb < n) {
-      const int len = min(32, n - jb);
-      if (WARP_ENV && jb < w0)
-        nb[c] = pair_chunk<PAIR_MOVED, MASKS>(P, B, jb, len, i, xi, yi, npos, nhd, opos, ohd, na_, oa, k_ex0, k_ex1, A, dupA, dupB, mrow_u);
-      else if (WARP_ENV && jb > w0)
-        nb[c] = pair_chunk<PAIR_UNMOVED, MASKS>(P, B, jb, len, i, xi, yi, npos, nhd, opos, ohd, na_, oa, k_ex0, k_ex1, A, dupA, dupB, mrow_u);
-      else
-        nb[c] = pair_chunk<PAIR_MIXED, MASKS>(P, B, jb, len, i, xi, yi, npos, nhd, opos, ohd, na_, oa, k_ex0, k_ex1, A, dupA, dupB, mrow_u);
+      if (WARP_ENV) {  // n % 32 == 0: full chunks, warp-uniform kind
+        if (jb < w0) nbits = pair_chunk<PAIR_MOVED, true, MASKS>(P, B, V, jb, 32, i, xi, yi, xf, yf, far_env, k_ex0, k_ex1, A, dup, mrow_u);
+        else if (jb > w0) nbits = pair_chunk<PAIR_UNMOVED, true, MASKS>(P, B, V, jb, 32, i, xi, yi, xf, yf, far_env, k_ex0, k_ex1, A, dup, mrow_u);
+        else nbits = pair_chunk<PAIR_MIXED, true, MASKS>(P, B, V, jb, 32, i, xi, yi, xf, yf, far_env, k_ex0, k_ex1, A, dup, mrow_u);
+      } else {
+        nbits = pair_chunk<PAIR_MIXED, false, MASKS>(P, B, V, jb, min(32, n - jb), i, xi, yi, xf, yf, far_env, k_ex0, k_ex1, A, dup, mrow_u);
+      }
     }
+    O.nb[c] = nbits;
   }
 
-  // ---- 12-d local state (uav.py:156-190): means of the lists (row weights are all 1 here), -1 blocks when empty
+  // ---- communication part of the local state (uav.py:162-172)
   if (A.cnt) {
     const double k = (double)A.cnt;
+    const int ai = V.na_()[i];
     ob[0] = (float)(A.sx / P.dc / k);
     ob[1] = (float)(A.sy / P.dc / k);
     ob[2] = (float)((A.sc - k * chi) / k);
@@ -278,33 +406,23 @@ __device__ __forceinline__ void agent_fast(const KParams &P, const UavSimBuffers
   } else {
     ob[0] = ob[1] = ob[2] = ob[3] = ob[4] = -1.f;
   }
-  if (nobs) {
-    const double k = (double)nobs;
-    ob[5] = (float)(ox / P.dp / k);
-    ob[6] = (float)(oy / P.dp / k);
-    ob[7] = (float)((ovx - k * chi) / k);
-    ob[8] = (float)((ovy - k * shi) / k);
-  } else {
-    ob[5] = ob[6] = ob[7] = ob[8] = -1.f;
-  }
-  O.tt = (double)ttf;
-  O.dup = -0.5 * ((double)dupA + (double)dupB);
-  O.nb[0] = nb[0]; O.nb[1] = nb[1]; O.nb[2] = nb[2]; O.nb[3] = nb[3];
+  O.dup = -0.5 * dup;
 }
 
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
 template <int CN, int CM, bool MASKS>
-__global__ void __launch_bounds__(NT, 2)
+__global__ void __launch_bounds__(NT, 3)
 uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restrict__ g_dth, int64_t env_begin,
                    int64_t env_count, int epb, int mode, double coop, int done_flag,
                    double *__restrict__ stats_partial) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = CN ? CN : P.n, m = CM ? CM : P.m;
   constexpr bool WARP_ENV = (CN > 0) && (CN % 32 == 0);
+  const EnvLayout L = (CN && CM) ? env_layout(CN, CM) : env_layout(n, m);
   const int tid = threadIdx.x;
-  const StepSmem S = carve(smem_raw, n, m, P.na, epb);
+  const CtaSmem S = carve(smem_raw, n, m, P.na, epb, L.stride);
   const int64_t plane = P.E * n;  // rew4 plane stride
 
   for (int k = tid; k < 3 * P.na; k += NT) S.dth[k] = g_dth[k];
@@ -317,11 +435,14 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
   for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
     const int64_t e0 = env_begin + grp * epb;
     const int ne = (int)min((int64_t)epb, env_begin + env_count - e0);
-    __syncthreads();  // previous iteration's readers are done; dth table visible
+    if (tid < epb) S.far[tid] = 0;  // (every phase-1 reader of the previous iteration has passed a barrier)
+    __syncthreads();                // previous iteration's readers are done; dth table visible
 
     // ---- phase 0a: targets (src/agent/target.py:27-60) ----
     for (int q = tid; q < ne * m; q += NT) {
       const int64_t gi = e0 * m + q;
+      const int te = q / m, t = q - te * m;
+      const EnvView V{S.env + (size_t)te * L.stride, L};
       double x = B.tx[gi], y = B.ty[gi], h = B.th[gi];
       double sh, ch;
       sincos(h, &sh, &ch);
@@ -335,9 +456,11 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
       }
       if (refl) { sincos(h, &sh, &ch); B.th[gi] = h; }
       B.tx[gi] = x; B.ty[gi] = y;
-      S.tpos[q] = make_double2(x, y);
+      V.tpos()[t] = make_double2(x, y);
       // cos(target.h) * target.v_max / self.v_max  (src/agent/uav.py:115-116)
-      S.tvel[q] = make_double2(ch * P.tv / P.uv, sh * P.tv / P.uv);
+      V.tvel()[t] = make_double2(ch * P.tv / P.uv, sh * P.tv / P.uv);
+      V.tposf()[t] = make_float2((float)(x - P.cx), (float)(y - P.cy));
+      if (!(fabs(x - P.cx) <= P.rmax && fabs(y - P.cy) <= P.rmax)) S.far[te] = 1;
       S.tcnt[q] = 0;
     }
     // ---- phase 0b: UAV kinematics (src/agent/uav.py:73-99) ----
@@ -345,12 +468,13 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
     const bool active = q < ne * n;
     const int el = active ? q / n : 0, i = q - el * n;
     const int64_t ge = e0 + el, gi = e0 * n + q;
+    const EnvView V{S.env + (size_t)el * L.stride, L};
     if (active) {
       double x = B.ux[gi], y = B.uy[gi], h = B.uh[gi];
       const int a_old = B.ua[gi], act = B.actions[gi];
       double sh, ch;
       sincos(h, &sh, &ch);
-      S.opos[q] = make_double2(x, y); S.ohd[q] = make_double2(ch, sh); S.oa[q] = a_old;
+      V.opos()[i] = make_double2(x, y); V.ohd()[i] = make_double2(ch, sh); V.oa()[i] = a_old;
       x += P.dtv_u * ch;
       y += P.dtv_u * sh;
       h += S.dth[3 * act];
@@ -358,8 +482,12 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
       // cos/sin of the new heading by angle addition (|error| ~ 3e-16; they only feed the observation).
       // The next step re-evaluates sincos from the stored heading, so the trajectory is unaffected.
       const double cd = S.dth[3 * act + 1], sd = S.dth[3 * act + 2];
-      const double chn = ch * cd - sh * sd, shn = sh * cd + ch * sd;
-      S.npos[q] = make_double2(x, y); S.nhd[q] = make_double2(chn, shn); S.na_[q] = act;
+      V.npos()[i] = make_double2(x, y);
+      V.nhd()[i] = make_double2(ch * cd - sh * sd, sh * cd + ch * sd);
+      V.na_()[i] = act;
+      V.nposf()[i] = make_float2((float)(x - P.cx), (float)(y - P.cy));
+      // the prefilter's error bound assumes every entity within rmax of the map centre
+      if (!(fabs(x - P.cx) <= P.rmax && fabs(y - P.cy) <= P.rmax)) S.far[el] = 1;
       B.ux[gi] = x; B.uy[gi] = y; B.uh[gi] = h; B.ua[gi] = act;
     }
     __syncthreads();
@@ -369,21 +497,15 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
     O.tt = 0; O.dup = 0; O.nb[0] = O.nb[1] = O.nb[2] = O.nb[3] = 0;
     double raw = 0, ttn = 0, bpn = 0, dupn = 0;
     if (active) {
-      const double2 me = S.npos[q], mh = S.nhd[q];
-      const double xi = me.x, yi = me.y, chi = mh.x, shi = mh.y;
-      const int ai = S.na_[q];
+      const double2 me = V.npos()[i];
+      const double xi = me.x, yi = me.y;
+      const int ai = V.na_()[i];
       float *ob = S.obs + (size_t)q * 12;
       const int64_t mrow_t = (ge * n + i) * m, mrow_u = (ge * n + i) * n;
       // row weights differ from 1 only if |x| < 2 and |y| < 2 (|rx|,|ry| <= 1 for any row in range)
       const bool near_origin = fabs(xi) < 2.0 && fabs(yi) < 2.0;
-      if (near_origin)
-        agent_exact<MASKS>(P, B, xi, yi, chi, shi, ai, i, n, m, S.tpos + el * m, S.tvel + el * m, S.npos + el * n,
-                           S.nhd + el * n, S.opos + el * n, S.ohd + el * n, S.na_ + el * n, S.oa + el * n,
-                           S.tcnt + el * m, ob, mrow_t, mrow_u, O);
-      else
-        agent_fast<CN, CM, WARP_ENV, MASKS>(P, B, xi, yi, chi, shi, ai, i, n, m, S.tpos + el * m, S.tvel + el * m,
-                                            S.npos + el * n, S.nhd + el * n, S.opos + el * n, S.ohd + el * n,
-                                            S.na_ + el * n, S.oa + el * n, S.tcnt + el * m, ob, mrow_t, mrow_u, O);
+      if (near_origin) agent_exact<MASKS>(P, B, V, S.tcnt + el * m, i, n, m, ob, mrow_t, mrow_u, &O);
+      else agent_fast<CN, CM, WARP_ENV, MASKS>(P, B, V, S.tcnt + el * m, i, n, m, S.far[el] != 0, ob, mrow_t, mrow_u, O);
       if (MASKS) { B.comm_mask[mrow_u + i] = 0; B.nbr_mask[mrow_u + i] = 0; B.dup_mask[mrow_u + i] = 0; }
       ob[9] = (float)(xi / P.dc);
       ob[10] = (float)(yi / P.dc);

@@ -42,6 +42,21 @@ static int raise_dynamic_smem(const void *fn, int device, size_t bytes) {
   return 0;
 }
 
+// Guarded fp32 squared threshold for the prefilter.  With coordinates c = fp32(x - centre), |x - centre| <= rmax:
+//   coordinate rounding  e_c <= rmax * 2^-24
+//   difference           |dx_f - dx| <= 2 e_c + |dx| 2^-24              =: e_d   (for |dx| <= thr)
+//   squared distance     |d2_f - d2| <= 2 sqrt(2) thr e_d + 2 e_d^2 + 3 * 2^-24 * thr^2   (products, fma, sum)
+// A pair with d2 <= thr^2 therefore has d2_f <= thr^2 + that bound; twice the bound is used, rounded up to fp32.
+static float prefilter_threshold(double thr, double rmax) {
+  const double u = 1.0 / 16777216.0;
+  const double e_c = rmax * u, e_d = 2 * e_c + thr * u;
+  const double bound = 2 * 1.4142135623730951 * thr * e_d + 2 * e_d * e_d + 3 * u * thr * thr;
+  const double v = thr * thr * (1.0 + 1e-12) + 2 * bound + 1e-6;
+  float f = (float)v;
+  if ((double)f < v) f = nextafterf(f, INFINITY);
+  return nextafterf(f, INFINITY);
+}
+
 extern "C" int uavsim_abi_version(void) { return UAVSIM_ABI_VERSION; }
 extern "C" const char *uavsim_last_error(void) { return g_err; }
 extern "C" int64_t uavsim_launch_count(const uavsim_t *h) { return h ? h->launches : 0; }
@@ -89,6 +104,14 @@ extern "C" int uavsim_create(const UavSimParams *p, int64_t n_envs, int64_t env_
   k.alpha = p->alpha; k.beta = p->beta; k.gamma = p->gamma;
   k.tt_hi = (double)(2 * p->m_targets);
   k.dup_lo = -2.718281828459045 / 2 * p->n_uav;
+  // fp32 prefilter (step_kernel.cuh): coordinates relative to the map centre, valid while every entity is within
+  // rmax of it; the guard band bounds the fp32 error of the squared distance so no true hit is ever dropped
+  k.cx = p->x_max / 2; k.cy = p->y_max / 2;
+  k.rmax = 32768.0;
+  k.f_dp = prefilter_threshold(p->dp, k.rmax);
+  k.f_dc = prefilter_threshold(p->dc, k.rmax);
+  k.f_2dp = prefilter_threshold(2 * p->dp, k.rmax);
+  k.f_dcmv = prefilter_threshold(p->dc + fabs(k.dtv_u) * (1.0 + 1e-9), k.rmax);
 
   // per action: dt * discrete_action(a) (src/agent/uav.py:73-81, :96) in the reference's evaluation order,
   // plus its cosine / sine for the angle-addition update of the observation heading terms
