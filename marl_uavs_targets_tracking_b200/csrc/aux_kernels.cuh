@@ -69,17 +69,27 @@ __global__ void uavsim_stats_clear_kernel(double *stats, int count) {
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) stats[k] = 0.0;
 }
 
-// fixed-order reduction of the per-CTA slots (single thread: <= a few thousand adds per episode)
+// fixed-order reduction of the per-CTA slots: one CTA of 256 threads, strided partial sums then a shared-memory
+// tree (the association order depends only on `slots`, so totals are reproducible)
 __global__ void uavsim_stats_reduce_kernel(const double *__restrict__ partial, int slots, double *__restrict__ out) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  __shared__ double sh[256][STAT_W];
+  if (blockIdx.x != 0) return;
   double a[STAT_W] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int half = 0; half < 2; half++)
-    for (int s = 0; s < slots; s++) {
-      const double *p = partial + ((size_t)half * slots + s) * STAT_W;
-      for (int k = 0; k < 5; k++) a[k] += p[k];
-      a[5] = fmax(a[5], p[5]);
-      a[6] += p[6];
+  for (int s = threadIdx.x; s < 2 * slots; s += 256) {
+    const double *p = partial + (size_t)s * STAT_W;
+    for (int k = 0; k < 5; k++) a[k] += p[k];
+    a[5] = fmax(a[5], p[5]);
+    a[6] += p[6];
+  }
+  for (int k = 0; k < STAT_W; k++) sh[threadIdx.x][k] = a[k];
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) {
+      for (int k = 0; k < 5; k++) sh[threadIdx.x][k] += sh[threadIdx.x + w][k];
+      sh[threadIdx.x][5] = fmax(sh[threadIdx.x][5], sh[threadIdx.x + w][5]);
+      sh[threadIdx.x][6] += sh[threadIdx.x + w][6];
     }
-  for (int k = 0; k < STAT_W; k++) out[k] = a[k];
+    __syncthreads();
+  }
+  if (threadIdx.x < STAT_W) out[threadIdx.x] = sh[0][threadIdx.x];
 }
-

@@ -10,7 +10,6 @@
 #include "../../include/uavsim.h"
 #include "philox.cuh"
 
-#define NT 256       // threads per CTA, step kernel (one thread per UAV, NT/n environments per CTA)
 #define PMI_NT 256   // threads per CTA, PMI kernel
 #define STAT_W 8     // doubles per statistics slot
 
@@ -66,7 +65,7 @@ struct uavsim {
   double *d_stats8;   // [8] reduced
   double *h_stats8;   // pinned
   int stat_slots;
-  int epb, grid_max;
+  int epb, grid_max, nt;   // environments per CTA, resident CTAs, threads per CTA of the step kernel
   StepKernelFn step_fn[2];  // [MASKS]
   size_t smem_step;
   // pmi

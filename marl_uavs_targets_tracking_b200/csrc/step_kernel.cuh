@@ -244,12 +244,9 @@ __device__ __forceinline__ void prefilter(const float2 *__restrict__ pf, int len
 // Candidates: `cn` = evaluate j's NEW position exactly (needed up to dc if j moved first, else up to 2dp);
 // `co` = evaluate j's OLD position exactly (j moves later, communication range dc).  The old position is
 // within dt*v of the new one, so co is prefiltered on the NEW position with the threshold dc + dt*v.
-// Returns the neighbour bits (d <= dp) of the chunk.
-template <int KIND, bool FULL, bool MASKS>
-__device__ __forceinline__ uint32_t pair_chunk(const KParams &P, const UavSimBuffers &B, const EnvView V, int jb, int len,
-                                               int i, double xi, double yi, float xf, float yf, bool far_env,
-                                               float k_ex0, float k_ex1, CommAcc &A, double &dup, int64_t mrow_u) {
-  uint32_t cn, co;
+template <int KIND, bool FULL>
+__device__ __forceinline__ void chunk_candidates(const KParams &P, const EnvView V, int jb, int len, int i, float xf,
+                                                 float yf, bool far_env, uint32_t &cn, uint32_t &co) {
   if (far_env) {
     cn = low_bits(len);
     co = cn;
@@ -274,10 +271,16 @@ __device__ __forceinline__ uint32_t pair_chunk(const KParams &P, const UavSimBuf
     cn &= ~self;
     co &= ~(lt | self);
   }
+}
+
+// (B, sparse) exact fp64 evaluation of the candidates only, ascending j like the reference's loops.
+// Each lane walks its own bits; the warp runs max-over-lanes iterations.  Returns the neighbour bits (d <= dp).
+template <int KIND, bool MASKS>
+__device__ __forceinline__ uint32_t pair_chunk_sparse(const KParams &P, const UavSimBuffers &B, const EnvView V, int jb,
+                                                      int len, int i, double xi, double yi, uint32_t cn, uint32_t co,
+                                                      float k_ex0, float k_ex1, CommAcc &A, double &dup, int64_t mrow_u) {
   if (MASKS)
     for (int jj = 0; jj < len; jj++) { B.comm_mask[mrow_u + jb + jj] = 0; B.nbr_mask[mrow_u + jb + jj] = 0; B.dup_mask[mrow_u + jb + jj] = 0; }
-
-  // ---- (B) exact fp64 evaluation of the candidates, ascending j like the reference's loops
   const double2 *npos = V.npos(), *nhd = V.nhd(), *opos = V.opos(), *ohd = V.ohd();
   uint32_t todo = cn | co, nbits = 0;
   while (todo) {
@@ -315,6 +318,73 @@ __device__ __forceinline__ uint32_t pair_chunk(const KParams &P, const UavSimBuf
     if (MASKS) B.comm_mask[mrow_u + j] = hc;
   }
   return nbits;
+}
+
+// (B, dense) when most partners of the chunk are candidates for some lane, walking every partner with
+// warp-uniform j (broadcast loads, no divergence, predicated accumulation) is cheaper than per-lane lists.
+// Full 32-partner chunks only (n % 32 == 0).
+template <int KIND, bool MASKS>
+__device__ __forceinline__ uint32_t pair_chunk_dense(const KParams &P, const UavSimBuffers &B, const EnvView V, int jb,
+                                                     int i, double xi, double yi, float k_ex0, float k_ex1, CommAcc &A,
+                                                     double &dup, int64_t mrow_u) {
+  const double2 *npos = V.npos(), *nhd = V.nhd(), *opos = V.opos(), *ohd = V.ohd();
+  const int *na_ = V.na_(), *oa = V.oa();
+  uint32_t bits = 0, bit = 1;
+  float dupA = 0.f, dupB = 0.f;  // two short fp32 partial sums per chunk (<= 16 terms each)
+  auto body = [&](int j, float &dupacc) {
+    const double2 np = npos[j];
+    const double dxn = np.x - xi, dyn = np.y - yi;
+    const double d2n = dxn * dxn + dyn * dyn;
+    const bool valid = (KIND != PAIR_MIXED) || (j != i);
+    const bool hd = valid && (d2n <= P.s_2dp_le);  // uav.py:225
+    const bool hn = valid && (d2n <= P.s_dp_le);   // uav.py:305
+    const float v = fast_ex2f(fmaf(fast_sqrtf((float)d2n), k_ex1, k_ex0));  // exp((2dp - d)/(2dp))
+    dupacc += hd ? v : 0.f;
+    if (hn) bits |= bit;
+    bit += bit;
+    bool hc;
+    if (KIND == PAIR_MOVED) {
+      hc = d2n <= P.s_dc_le;  // uav.py:135, partner already at its new state
+      if (hc) { const double2 h = nhd[j]; A.sx += dxn; A.sy += dyn; A.sc += h.x; A.ss += h.y; A.sa += na_[j]; A.cnt++; }
+    } else {
+      const double2 op = opos[j];
+      const double dxo = op.x - xi, dyo = op.y - yi;
+      const double d2o = dxo * dxo + dyo * dyo;
+      if (KIND == PAIR_UNMOVED) {
+        hc = d2o <= P.s_dc_le;  // partner still at its old state
+        if (hc) { const double2 h = ohd[j]; A.sx += dxo; A.sy += dyo; A.sc += h.x; A.ss += h.y; A.sa += oa[j]; A.cnt++; }
+      } else {
+        const bool hc_new = (j < i) && (d2n <= P.s_dc_le);
+        const bool hc_old = (j > i) && (d2o <= P.s_dc_le);
+        if (hc_new) { const double2 h = nhd[j]; A.sx += dxn; A.sy += dyn; A.sc += h.x; A.ss += h.y; A.sa += na_[j]; A.cnt++; }
+        if (hc_old) { const double2 h = ohd[j]; A.sx += dxo; A.sy += dyo; A.sc += h.x; A.ss += h.y; A.sa += oa[j]; A.cnt++; }
+        hc = hc_new || hc_old;
+      }
+    }
+    if (MASKS) { B.comm_mask[mrow_u + j] = hc; B.nbr_mask[mrow_u + j] = hn; B.dup_mask[mrow_u + j] = hd; }
+  };
+#pragma unroll 2
+  for (int j = jb; j < jb + 32; j += 2) { body(j, dupA); body(j + 1, dupB); }
+  dup += (double)dupA + (double)dupB;
+  return bits;
+}
+
+// chunk dispatch: prefilter, then the dense or the sparse exact pass.  DENSE_OK: all 32 lanes of the warp are
+// active and work on the same environment, so the choice can be made warp-uniform with one redux.
+template <int KIND, bool FULL, bool DENSE_OK, bool MASKS>
+__device__ __forceinline__ uint32_t pair_chunk(const KParams &P, const UavSimBuffers &B, const EnvView V, int jb, int len,
+                                               int i, double xi, double yi, float xf, float yf, bool far_env,
+                                               float k_ex0, float k_ex1, CommAcc &A, double &dup, int64_t mrow_u) {
+  uint32_t cn, co;
+  chunk_candidates<KIND, FULL>(P, V, jb, len, i, xf, yf, far_env, cn, co);
+  if (DENSE_OK) {
+    // per-lane list length; the sparse pass costs ~max(len) * 60 instructions, the dense one ~32 * (26..40)
+    const int pop = __popc(cn | co);
+    const int maxpop = __reduce_max_sync(0xffffffffu, pop);
+    const int limit = (KIND == PAIR_MOVED) ? 12 : 18;
+    if (maxpop > limit) return pair_chunk_dense<KIND, MASKS>(P, B, V, jb, i, xi, yi, k_ex0, k_ex1, A, dup, mrow_u);
+  }
+  return pair_chunk_sparse<KIND, MASKS>(P, B, V, jb, len, i, xi, yi, cn, co, k_ex0, k_ex1, A, dup, mrow_u);
 }
 
 template <int CN, int CM, bool WARP_ENV, bool MASKS>
@@ -384,11 +454,11 @@ __device__ __forceinline__ void agent_fast(const KParams &P, const UavSimBuffers
     uint32_t nbits = 0;
     if (jb < n) {
       if (WARP_ENV) {  // n % 32 == 0: full chunks, warp-uniform kind
-        if (jb < w0) nbits = pair_chunk<PAIR_MOVED, true, MASKS>(P, B, V, jb, 32, i, xi, yi, xf, yf, far_env, k_ex0, k_ex1, A, dup, mrow_u);
-        else if (jb > w0) nbits = pair_chunk<PAIR_UNMOVED, true, MASKS>(P, B, V, jb, 32, i, xi, yi, xf, yf, far_env, k_ex0, k_ex1, A, dup, mrow_u);
-        else nbits = pair_chunk<PAIR_MIXED, true, MASKS>(P, B, V, jb, 32, i, xi, yi, xf, yf, far_env, k_ex0, k_ex1, A, dup, mrow_u);
+        if (jb < w0) nbits = pair_chunk<PAIR_MOVED, true, true, MASKS>(P, B, V, jb, 32, i, xi, yi, xf, yf, far_env, k_ex0, k_ex1, A, dup, mrow_u);
+        else if (jb > w0) nbits = pair_chunk<PAIR_UNMOVED, true, true, MASKS>(P, B, V, jb, 32, i, xi, yi, xf, yf, far_env, k_ex0, k_ex1, A, dup, mrow_u);
+        else nbits = pair_chunk<PAIR_MIXED, true, true, MASKS>(P, B, V, jb, 32, i, xi, yi, xf, yf, far_env, k_ex0, k_ex1, A, dup, mrow_u);
       } else {
-        nbits = pair_chunk<PAIR_MIXED, false, MASKS>(P, B, V, jb, min(32, n - jb), i, xi, yi, xf, yf, far_env, k_ex0, k_ex1, A, dup, mrow_u);
+        nbits = pair_chunk<PAIR_MIXED, false, false, MASKS>(P, B, V, jb, min(32, n - jb), i, xi, yi, xf, yf, far_env, k_ex0, k_ex1, A, dup, mrow_u);
       }
     }
     O.nb[c] = nbits;
@@ -412,8 +482,8 @@ __device__ __forceinline__ void agent_fast(const KParams &P, const UavSimBuffers
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <int CN, int CM, bool MASKS>
-__global__ void __launch_bounds__(NT, 3)
+template <int CN, int CM, bool MASKS, int NT>
+__global__ void __launch_bounds__(NT, 768 / NT)
 uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restrict__ g_dth, int64_t env_begin,
                    int64_t env_count, int epb, int mode, double coop, int done_flag,
                    double *__restrict__ stats_partial) {

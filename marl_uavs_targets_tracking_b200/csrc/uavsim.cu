@@ -127,11 +127,15 @@ extern "C" int uavsim_create(const UavSimParams *p, int64_t n_envs, int64_t env_
   CUDA_TRY(cudaMemcpy(h->d_dth, dth, sizeof(double) * 3 * p->na, cudaMemcpyHostToDevice));
   free(dth);
 
-  // launch geometry of the step kernel
-  int epb = NT / p->n_uav;
+  // launch geometry of the step kernel: one thread per UAV, nt / n environments per CTA.  Small CTAs keep the
+  // phase barriers cheap (the exact pass has data-dependent length); compile-time sizes for the two headline scenarios
+  if (k.n == 64 && k.m == 64) { h->nt = 64; h->step_fn[0] = uavsim_step_kernel<64, 64, false, 64>; h->step_fn[1] = uavsim_step_kernel<64, 64, true, 64>; }
+  else if (k.n == 10 && k.m == 10) { h->nt = 128; h->step_fn[0] = uavsim_step_kernel<10, 10, false, 128>; h->step_fn[1] = uavsim_step_kernel<10, 10, true, 128>; }
+  else { h->nt = 128; h->step_fn[0] = uavsim_step_kernel<0, 0, false, 128>; h->step_fn[1] = uavsim_step_kernel<0, 0, true, 128>; }
+  int epb = h->nt / p->n_uav;
   if (epb < 1) epb = 1;
   if ((int64_t)epb > n_envs) epb = (int)n_envs;
-  while (epb > 1 && step_smem_bytes(k.n, k.m, k.na, epb) > 100 * 1024) epb--;
+  while (epb > 1 && step_smem_bytes(k.n, k.m, k.na, epb) > 64 * 1024) epb--;
   h->epb = epb;
   h->smem_step = step_smem_bytes(k.n, k.m, k.na, epb);
   if (h->smem_step > 227 * 1024) {
@@ -139,19 +143,15 @@ extern "C" int uavsim_create(const UavSimParams *p, int64_t n_envs, int64_t env_
     free(h);
     return UAVSIM_ERR_UNSUPPORTED;
   }
-  // compile-time sizes for the two headline scenarios, run-time sizes otherwise
-  if (k.n == 64 && k.m == 64) { h->step_fn[0] = uavsim_step_kernel<64, 64, false>; h->step_fn[1] = uavsim_step_kernel<64, 64, true>; }
-  else if (k.n == 10 && k.m == 10) { h->step_fn[0] = uavsim_step_kernel<10, 10, false>; h->step_fn[1] = uavsim_step_kernel<10, 10, true>; }
-  else { h->step_fn[0] = uavsim_step_kernel<0, 0, false>; h->step_fn[1] = uavsim_step_kernel<0, 0, true>; }
   for (int v = 0; v < 2; v++) {
     int rc = raise_dynamic_smem((const void *)h->step_fn[v], device, h->smem_step);
     if (rc) return rc;
   }
   int occ = 1;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->step_fn[0], NT, h->smem_step));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->step_fn[0], h->nt, h->smem_step));
   if (occ < 1) occ = 1;
   h->grid_max = h->sm_count * occ;
-  h->stat_slots = h->grid_max > 1024 ? h->grid_max : 1024;
+  h->stat_slots = h->grid_max > 4096 ? h->grid_max : 4096;
   CUDA_TRY(cudaMalloc(&h->d_stats, sizeof(double) * 2 * h->stat_slots * STAT_W));
   CUDA_TRY(cudaMalloc(&h->d_stats8, sizeof(double) * 8));
   CUDA_TRY(cudaMallocHost(&h->h_stats8, sizeof(double) * 8));
@@ -361,7 +361,7 @@ extern "C" int uavsim_set_pmi_weights(uavsim_t *h, const UavSimPmiWeights *w, vo
 static int launch_step_range(uavsim_t *h, int mode, double coop, int64_t e0, int64_t cnt, int done_flag, cudaStream_t st) {
   const int64_t ngroups = (cnt + h->epb - 1) / h->epb;
   const int grid = (int)(ngroups < h->grid_max ? ngroups : h->grid_max);
-  h->step_fn[h->buf.obs_mask ? 1 : 0]<<<grid, NT, h->smem_step, st>>>(h->kp, h->buf, h->d_dth, e0, cnt, h->epb, mode, coop, done_flag, h->d_stats);
+  h->step_fn[h->buf.obs_mask ? 1 : 0]<<<grid, h->nt, h->smem_step, st>>>(h->kp, h->buf, h->d_dth, e0, cnt, h->epb, mode, coop, done_flag, h->d_stats);
   CUDA_TRY(cudaGetLastError());
   h->launches++;
   if (mode == UAVSIM_MODE_PMI && coop != 0.0) return pmi_launch(h, e0, cnt, coop, st, false);
@@ -432,7 +432,7 @@ extern "C" int uavsim_episode_stats(uavsim_t *h, double out[8], void *stream) {
   if (!h || !out) { SET_ERR("uavsim_episode_stats: NULL argument"); return UAVSIM_ERR_ARG; }
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  uavsim_stats_reduce_kernel<<<1, 32, 0, st>>>(h->d_stats, h->stat_slots, h->d_stats8);
+  uavsim_stats_reduce_kernel<<<1, 256, 0, st>>>(h->d_stats, h->stat_slots, h->d_stats8);
   CUDA_TRY(cudaGetLastError());
   h->launches++;
   CUDA_TRY(cudaMemcpyAsync(h->h_stats8, h->d_stats8, sizeof(double) * 8, cudaMemcpyDeviceToHost, st));
