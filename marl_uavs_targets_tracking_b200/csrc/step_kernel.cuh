@@ -573,7 +573,9 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
       float *ob = S.obs + (size_t)q * 12;
       const int64_t mrow_t = (ge * n + i) * m, mrow_u = (ge * n + i) * n;
       // row weights differ from 1 only if |x| < 2 and |y| < 2 (|rx|,|ry| <= 1 for any row in range)
-      const bool near_origin = fabs(xi) < 2.0 && fabs(yi) < 2.0;
+      bool near_origin = fabs(xi) < 2.0 && fabs(yi) < 2.0;
+      // the fast path uses warp-wide intrinsics when the warp lies inside one environment: keep the branch uniform
+      if (WARP_ENV) near_origin = __any_sync(0xffffffffu, near_origin);
       if (near_origin) agent_exact<MASKS>(P, B, V, S.tcnt + el * m, i, n, m, ob, mrow_t, mrow_u, &O);
       else agent_fast<CN, CM, WARP_ENV, MASKS>(P, B, V, S.tcnt + el * m, i, n, m, S.far[el] != 0, ob, mrow_t, mrow_u, O);
       if (MASKS) { B.comm_mask[mrow_u + i] = 0; B.nbr_mask[mrow_u + i] = 0; B.dup_mask[mrow_u + i] = 0; }

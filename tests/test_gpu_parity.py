@@ -123,6 +123,50 @@ def test_cuda_matches_oracle_on_seeded_batches(oracle, n, m, method, E, T):
     env.close()
 
 
+def test_origin_corner_in_the_warp_uniform_kernel(oracle):
+    """64x64 kernel (warp = 32 UAVs of one environment): a UAV inside the 4 m x 4 m origin corner switches its
+    whole warp to the exact per-row path; results must still match the oracle (weight quirk, uav.py:162-186)."""
+    from marl_uavs_targets_tracking_b200 import default_config
+    n = m = 64
+    cfg = default_config("MAAC-G", n, m)
+    env = _env(n, m, cfg, 6, track_counts=True, seed=9)
+    env.reset(cfg)
+    st = env.get_state()
+    st["ux"][1, 5], st["uy"][1, 5] = 0.5, 0.7
+    st["ux"][2, 40], st["uy"][2, 40] = -1.0, 1.5
+    st["ux"][2, 41], st["uy"][2, 41] = 30.0, 40.0     # a partner within dc of the corner UAV
+    st["tx"][1, 3], st["ty"][1, 3] = 50.0, 60.0        # a target within dp of it
+    st["uh"][1, 5] = 0.0  # moves +20 m in x: out of the corner after the first step, in it before
+    st["ux"][4, 7], st["uy"][4, 7], st["uh"][4, 7] = -19.5, 0.3, 0.0   # lands in the corner after the move
+    env.set_state(cfg, *(st[k] for k in ("ux", "uy", "uh", "ua", "tx", "ty", "th")))
+    P = oracle_params_from_config(cfg, n, m)
+    host = {k: np.ascontiguousarray(v.cpu().numpy()) for k, v in env.get_state().items()}
+    for t in range(4):
+        a = env.random_actions(3, t).cpu().numpy().copy()
+        obs, rew4, cov = env.step_device(cfg, None)
+        ref = oracle.step_batch(P, 1, float(cfg["cooperative"]), None, host, a, nthreads=4)
+        assert np.array_equal(cov.cpu().numpy(), ref["covered"])
+        assert np.array_equal(env.tracker_counts.cpu().numpy(), ref["tracker_cnt"])
+        assert max_scaled_err(obs.double().cpu().numpy(), ref["obs"]) <= TOL_TIGHT
+        assert max_scaled_err(rew4.double().cpu().numpy(), ref["rew4"]) <= TOL_TIGHT
+    env.close()
+
+
+def test_long_episode_64x64_does_not_stall():
+    """A full 200-step episode at 64x64 with many environments (UAVs do reach the origin corner)."""
+    from marl_uavs_targets_tracking_b200 import default_config
+    cfg = default_config("MAAC-G", 64, 64)
+    env = _env(64, 64, cfg, 4096, seed=5)
+    env.reset(cfg)
+    for t in range(200):
+        env.random_actions(8, t)
+        env.step_device(cfg, None)
+    torch.cuda.synchronize()
+    s = env.episode_stats()
+    assert s["env_steps"] == 4096 * 200
+    env.close()
+
+
 def test_reset_and_random_policy_match_philox_reference():
     from marl_uavs_targets_tracking_b200 import default_config
     from philox_ref import actions_reference, reset_reference
