@@ -236,19 +236,28 @@ def measure_workload(torch, dist, env_cls, args, name, rank, world, device, step
     sampler = ClockSampler(device.index)
     sampler.start()
     ev0.record(torch.cuda.current_stream(device))
+    marks = []
     for i in range(steps):
         one_step(warmup + i)
+        if args.trace_every and (i + 1) % args.trace_every == 0:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(torch.cuda.current_stream(device))
+            marks.append(e)
     ev1.record(torch.cuda.current_stream(device))
     barrier()
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
     launches = env.launch_count() - l0
+    trace = None
+    if marks:  # ms per step over consecutive windows of the timed region (diagnostic only)
+        pts = [ev0] + marks
+        trace = [round(pts[k].elapsed_time(pts[k + 1]) / args.trace_every, 4) for k in range(len(marks))]
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     res = {"name": name, "desc": desc, "n": n, "m": m, "E": E, "method": method, "ms": ms, "steps": steps,
-           "launches": launches, "clocks": clocks, "value": E * world * n * steps / (ms * 1e-3)}
+           "launches": launches, "clocks": clocks, "value": E * world * n * steps / (ms * 1e-3), "trace": trace}
 
     if with_e2e:
         h_act = torch.empty((NB, E, n), dtype=torch.int32).pin_memory()
@@ -291,6 +300,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=8, help="env ranges the host-buffer step is pipelined over")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU time spent on the cpu_baseline sample")
+    ap.add_argument("--trace-every", type=int, default=0, help="also report ms/step per window of this many steps")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads and the CPU baseline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
@@ -352,6 +362,8 @@ def main():
                             "bytes_per_launch": bytes_per_launch,
                             "bytes_per_agent_step": alg_bytes_per_env_step(n, m) / n},
                "episode_stats": main_res["episode_stats"], "other_workloads": extras}
+        if main_res.get("trace"):
+            out["ms_per_step_trace"] = {"every": args.trace_every, "ms": main_res["trace"]}
         if world == 1 and not args.no_extras:
             v, sample, _, _, _ = cpu_oracle_rate(n, m, main_res["method"], args.cpu_seconds, os.cpu_count() or 1)
             out["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": os.cpu_count() or 1, "kind": "port",

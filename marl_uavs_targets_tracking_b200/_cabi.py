@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libuavsim.so")
+LIB_PATH = os.environ.get("UAVSIM_LIB") or os.path.join(_HERE, "csrc", "libuavsim.so")  # UAVSIM_LIB: tuning builds
 
 MODE_SELF, MODE_MEAN, MODE_PMI = 0, 1, 2
 OBS_DIM = 12

@@ -26,6 +26,11 @@
 #pragma once
 #include "common.cuh"
 
+// tuning knobs (overridable with -D for experiments)
+#ifndef UAVSIM_NT64
+#define UAVSIM_NT64 64   // threads per CTA of the 64x64 kernel
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // shared memory: one block per environment (byte offsets below), then CTA-wide arrays
 // ------------------------------------------------------------------------------------------------
@@ -99,6 +104,9 @@ struct EnvView {
   __device__ __forceinline__ int *na_() const { return reinterpret_cast<int *>(b + L.na_); }
   __device__ __forceinline__ int *oa() const { return reinterpret_cast<int *>(b + L.oa); }
 };
+
+// one copy of the fp64 sincos code for both call sites (instruction-fetch footprint)
+__device__ __noinline__ void sincos_shared(double h, double *s, double *c) { sincos(h, s, c); }
 
 // what phase 1 produces for one UAV
 struct AgentOut {
@@ -204,85 +212,73 @@ struct CommAcc {
   int sa, cnt;
 };
 
-enum { PAIR_MOVED = 0, PAIR_MIXED = 1, PAIR_UNMOVED = 2 };
-
 __device__ __forceinline__ uint32_t low_bits(int len) { return len >= 32 ? 0xffffffffu : ((1u << len) - 1u); }
 
-// (A) fp32 prefilter over one chunk of partner positions: up to three candidate masks for three guarded
-// thresholds t0 <= t1 <= t2 (unused ones are compiled out).  FULL: the chunk has exactly 32 entries
-// (compile-time bits, fully unrolled).
-template <bool FULL, bool W0, bool W1, bool W2>
+// (A) fp32 prefilter over one chunk of partner positions: three candidate masks for three guarded thresholds
+// t0 <= t1 <= t2.  Code size matters here (the kernel is instruction-fetch sensitive): 8 partners per loop
+// trip with compile-time bits, the byte shifted into place once per trip.
 __device__ __forceinline__ void prefilter(const float2 *__restrict__ pf, int len, float xf, float yf, float t0, float t1,
                                           float t2, uint32_t &m0, uint32_t &m1, uint32_t &m2) {
   m0 = m1 = m2 = 0;
-  if (FULL) {
+  int jj = 0;
+#pragma unroll 1
+  for (; jj + 8 <= len; jj += 8) {
+    uint32_t b0 = 0, b1 = 0, b2 = 0;
 #pragma unroll
-    for (int jj = 0; jj < 32; jj++) {
-      const float2 p = pf[jj];
+    for (int u = 0; u < 8; u++) {
+      const float2 p = pf[jj + u];
       const float dx = p.x - xf, dy = p.y - yf;
       const float d2 = fmaf(dx, dx, dy * dy);
-      if (W0) m0 |= (d2 <= t0) ? (1u << jj) : 0u;
-      if (W1) m1 |= (d2 <= t1) ? (1u << jj) : 0u;
-      if (W2) m2 |= (d2 <= t2) ? (1u << jj) : 0u;
+      b0 |= (d2 <= t0) ? (1u << u) : 0u;
+      b1 |= (d2 <= t1) ? (1u << u) : 0u;
+      b2 |= (d2 <= t2) ? (1u << u) : 0u;
     }
-  } else {
-    for (int jj = 0; jj < len; jj++) {
-      const float2 p = pf[jj];
-      const float dx = p.x - xf, dy = p.y - yf;
-      const float d2 = fmaf(dx, dx, dy * dy);
-      if (W0) m0 |= (d2 <= t0) ? (1u << jj) : 0u;
-      if (W1) m1 |= (d2 <= t1) ? (1u << jj) : 0u;
-      if (W2) m2 |= (d2 <= t2) ? (1u << jj) : 0u;
-    }
+    m0 |= b0 << jj; m1 |= b1 << jj; m2 |= b2 << jj;
+  }
+#pragma unroll 1
+  for (; jj < len; jj++) {
+    const float2 p = pf[jj];
+    const float dx = p.x - xf, dy = p.y - yf;
+    const float d2 = fmaf(dx, dx, dy * dy);
+    m0 |= (d2 <= t0) ? (1u << jj) : 0u;
+    m1 |= (d2 <= t1) ? (1u << jj) : 0u;
+    m2 |= (d2 <= t2) ? (1u << jj) : 0u;
   }
 }
 
-// One chunk of up to 32 partner UAVs j = jb .. jb+len-1 for UAV i.
-//   PAIR_MOVED    every j moved before i (j < i): its new state serves the reward tests and communication
-//   PAIR_UNMOVED  every j moves after i: new-new distance for the rewards, new-old for communication
-//   PAIR_MIXED    per-lane order (j in the same warp as i, or a run-time sized environment)
+// One chunk of up to 32 partner UAVs j = jb .. jb+len-1 for UAV i.  Partners with j < i moved before i: their
+// new state serves the reward tests and communication; partners with j > i move after i: new-new distance for
+// the rewards, new-old distance for communication (uav.py:124-147 with the update order of environment.py:133-138).
 // Candidates: `cn` = evaluate j's NEW position exactly (needed up to dc if j moved first, else up to 2dp);
-// `co` = evaluate j's OLD position exactly (j moves later, communication range dc).  The old position is
-// within dt*v of the new one, so co is prefiltered on the NEW position with the threshold dc + dt*v.
-template <int KIND, bool FULL>
-__device__ __forceinline__ void chunk_candidates(const KParams &P, const EnvView V, int jb, int len, int i, float xf,
-                                                 float yf, bool far_env, uint32_t &cn, uint32_t &co) {
+// `co` = evaluate j's OLD position exactly (j > i, communication range dc).  The old position is within dt*v of
+// the new one, so co is prefiltered on the NEW position with the threshold dc + dt*v.
+// One generic routine for every chunk (kept small on purpose).  Returns the neighbour bits (d <= dp).
+template <bool MASKS>
+__device__ __forceinline__ uint32_t pair_chunk(const KParams &P, const UavSimBuffers &B, const EnvView V, int jb, int len,
+                                               int i, double xi, double yi, float xf, float yf, bool far_env,
+                                               float k_ex0, float k_ex1, CommAcc &A, double &dup, int64_t mrow_u) {
+  const int sj = i - jb;                                   // bits below sj moved before i, bits above move after
+  const uint32_t lt = sj <= 0 ? 0u : low_bits(sj);
+  const uint32_t self = (sj >= 0 && sj < 32) ? (1u << sj) : 0u;
+  uint32_t cn, co;
   if (far_env) {
-    cn = low_bits(len);
-    co = cn;
+    cn = co = low_bits(len);
   } else {
     uint32_t m_2dp, m_dc, m_dcmv;
-    prefilter<FULL, KIND != PAIR_MOVED, KIND != PAIR_UNMOVED, KIND != PAIR_MOVED>(V.nposf() + jb, len, xf, yf, P.f_2dp,
-                                                                                 P.f_dc, P.f_dcmv, m_2dp, m_dc, m_dcmv);
-    if (KIND == PAIR_MOVED) { cn = m_dc; co = 0; }
-    else if (KIND == PAIR_UNMOVED) { cn = m_2dp; co = m_dcmv; }
-    else {
-      const int sj = i - jb;  // bits below sj moved before i, bits above move after
-      const uint32_t lt = sj <= 0 ? 0u : low_bits(sj);
-      cn = (m_dc & lt) | (m_2dp & ~lt);
-      co = m_dcmv;
-    }
+    prefilter(V.nposf() + jb, len, xf, yf, P.f_2dp, P.f_dc, P.f_dcmv, m_2dp, m_dc, m_dcmv);
+    cn = (m_dc & lt) | (m_2dp & ~lt);
+    co = m_dcmv;
   }
-  if (KIND == PAIR_MOVED) co = 0;
-  if (KIND == PAIR_MIXED) {
-    const int sj = i - jb;
-    const uint32_t lt = sj <= 0 ? 0u : low_bits(sj);
-    const uint32_t self = (sj >= 0 && sj < 32) ? (1u << sj) : 0u;
-    cn &= ~self;
-    co &= ~(lt | self);
-  }
-}
-
-// (B, sparse) exact fp64 evaluation of the candidates only, ascending j like the reference's loops.
-// Each lane walks its own bits; the warp runs max-over-lanes iterations.  Returns the neighbour bits (d <= dp).
-template <int KIND, bool MASKS>
-__device__ __forceinline__ uint32_t pair_chunk_sparse(const KParams &P, const UavSimBuffers &B, const EnvView V, int jb,
-                                                      int len, int i, double xi, double yi, uint32_t cn, uint32_t co,
-                                                      float k_ex0, float k_ex1, CommAcc &A, double &dup, int64_t mrow_u) {
+  cn &= ~self;
+  co &= ~(lt | self);
   if (MASKS)
     for (int jj = 0; jj < len; jj++) { B.comm_mask[mrow_u + jb + jj] = 0; B.nbr_mask[mrow_u + jb + jj] = 0; B.dup_mask[mrow_u + jb + jj] = 0; }
+
+  // (B) exact fp64 evaluation of the candidates only, ascending j like the reference's loops.  Each lane walks
+  // its own bits; the warp runs max-over-lanes iterations.
   const double2 *npos = V.npos(), *nhd = V.nhd(), *opos = V.opos(), *ohd = V.ohd();
   uint32_t todo = cn | co, nbits = 0;
+#pragma unroll 1
   while (todo) {
     const int jj = __ffs((int)todo) - 1;
     const uint32_t bit = 1u << jj;
@@ -298,14 +294,13 @@ __device__ __forceinline__ uint32_t pair_chunk_sparse(const KParams &P, const Ua
       if (hd) dup += (double)fast_ex2f(fmaf(fast_sqrtf((float)d2n), k_ex1, k_ex0));  // exp((2dp - d)/(2dp))
       if (hn) nbits |= bit;
       if (MASKS) { B.nbr_mask[mrow_u + j] = hn; B.dup_mask[mrow_u + j] = hd; }
-      const bool moved = (KIND == PAIR_MOVED) || (KIND == PAIR_MIXED && j < i);
-      if (moved && d2n <= P.s_dc_le) {  // uav.py:135, partner already at its new state
+      if ((lt & bit) && d2n <= P.s_dc_le) {  // uav.py:135, partner already at its new state
         const double2 h = nhd[j];
         A.sx += dxn; A.sy += dyn; A.sc += h.x; A.ss += h.y; A.sa += V.na_()[j]; A.cnt++;
         hc = true;
       }
     }
-    if (KIND != PAIR_MOVED && (co & bit)) {
+    if (co & bit) {
       const double2 op = opos[j];
       const double dxo = op.x - xi, dyo = op.y - yi;
       const double d2o = dxo * dxo + dyo * dyo;
@@ -318,73 +313,6 @@ __device__ __forceinline__ uint32_t pair_chunk_sparse(const KParams &P, const Ua
     if (MASKS) B.comm_mask[mrow_u + j] = hc;
   }
   return nbits;
-}
-
-// (B, dense) when most partners of the chunk are candidates for some lane, walking every partner with
-// warp-uniform j (broadcast loads, no divergence, predicated accumulation) is cheaper than per-lane lists.
-// Full 32-partner chunks only (n % 32 == 0).
-template <int KIND, bool MASKS>
-__device__ __forceinline__ uint32_t pair_chunk_dense(const KParams &P, const UavSimBuffers &B, const EnvView V, int jb,
-                                                     int i, double xi, double yi, float k_ex0, float k_ex1, CommAcc &A,
-                                                     double &dup, int64_t mrow_u) {
-  const double2 *npos = V.npos(), *nhd = V.nhd(), *opos = V.opos(), *ohd = V.ohd();
-  const int *na_ = V.na_(), *oa = V.oa();
-  uint32_t bits = 0, bit = 1;
-  float dupA = 0.f, dupB = 0.f;  // two short fp32 partial sums per chunk (<= 16 terms each)
-  auto body = [&](int j, float &dupacc) {
-    const double2 np = npos[j];
-    const double dxn = np.x - xi, dyn = np.y - yi;
-    const double d2n = dxn * dxn + dyn * dyn;
-    const bool valid = (KIND != PAIR_MIXED) || (j != i);
-    const bool hd = valid && (d2n <= P.s_2dp_le);  // uav.py:225
-    const bool hn = valid && (d2n <= P.s_dp_le);   // uav.py:305
-    const float v = fast_ex2f(fmaf(fast_sqrtf((float)d2n), k_ex1, k_ex0));  // exp((2dp - d)/(2dp))
-    dupacc += hd ? v : 0.f;
-    if (hn) bits |= bit;
-    bit += bit;
-    bool hc;
-    if (KIND == PAIR_MOVED) {
-      hc = d2n <= P.s_dc_le;  // uav.py:135, partner already at its new state
-      if (hc) { const double2 h = nhd[j]; A.sx += dxn; A.sy += dyn; A.sc += h.x; A.ss += h.y; A.sa += na_[j]; A.cnt++; }
-    } else {
-      const double2 op = opos[j];
-      const double dxo = op.x - xi, dyo = op.y - yi;
-      const double d2o = dxo * dxo + dyo * dyo;
-      if (KIND == PAIR_UNMOVED) {
-        hc = d2o <= P.s_dc_le;  // partner still at its old state
-        if (hc) { const double2 h = ohd[j]; A.sx += dxo; A.sy += dyo; A.sc += h.x; A.ss += h.y; A.sa += oa[j]; A.cnt++; }
-      } else {
-        const bool hc_new = (j < i) && (d2n <= P.s_dc_le);
-        const bool hc_old = (j > i) && (d2o <= P.s_dc_le);
-        if (hc_new) { const double2 h = nhd[j]; A.sx += dxn; A.sy += dyn; A.sc += h.x; A.ss += h.y; A.sa += na_[j]; A.cnt++; }
-        if (hc_old) { const double2 h = ohd[j]; A.sx += dxo; A.sy += dyo; A.sc += h.x; A.ss += h.y; A.sa += oa[j]; A.cnt++; }
-        hc = hc_new || hc_old;
-      }
-    }
-    if (MASKS) { B.comm_mask[mrow_u + j] = hc; B.nbr_mask[mrow_u + j] = hn; B.dup_mask[mrow_u + j] = hd; }
-  };
-#pragma unroll 2
-  for (int j = jb; j < jb + 32; j += 2) { body(j, dupA); body(j + 1, dupB); }
-  dup += (double)dupA + (double)dupB;
-  return bits;
-}
-
-// chunk dispatch: prefilter, then the dense or the sparse exact pass.  DENSE_OK: all 32 lanes of the warp are
-// active and work on the same environment, so the choice can be made warp-uniform with one redux.
-template <int KIND, bool FULL, bool DENSE_OK, bool MASKS>
-__device__ __forceinline__ uint32_t pair_chunk(const KParams &P, const UavSimBuffers &B, const EnvView V, int jb, int len,
-                                               int i, double xi, double yi, float xf, float yf, bool far_env,
-                                               float k_ex0, float k_ex1, CommAcc &A, double &dup, int64_t mrow_u) {
-  uint32_t cn, co;
-  chunk_candidates<KIND, FULL>(P, V, jb, len, i, xf, yf, far_env, cn, co);
-  if (DENSE_OK) {
-    // per-lane list length; the sparse pass costs ~max(len) * 60 instructions, the dense one ~32 * (26..40)
-    const int pop = __popc(cn | co);
-    const int maxpop = __reduce_max_sync(0xffffffffu, pop);
-    const int limit = (KIND == PAIR_MOVED) ? 12 : 18;
-    if (maxpop > limit) return pair_chunk_dense<KIND, MASKS>(P, B, V, jb, i, xi, yi, k_ex0, k_ex1, A, dup, mrow_u);
-  }
-  return pair_chunk_sparse<KIND, MASKS>(P, B, V, jb, len, i, xi, yi, cn, co, k_ex0, k_ex1, A, dup, mrow_u);
 }
 
 template <int CN, int CM, bool WARP_ENV, bool MASKS>
@@ -403,14 +331,15 @@ __device__ __forceinline__ void agent_fast(const KParams &P, const UavSimBuffers
     double ox = 0, oy = 0, ovx = 0, ovy = 0, tt = 0;
     int nobs = 0;
     const double2 *tpos = V.tpos(), *tvel = V.tvel();
+#pragma unroll 1
     for (int tb = 0; tb < m; tb += 32) {
       const int len = min(32, m - tb);
       uint32_t ct, u1, u2;
       if (far_env) ct = low_bits(len);
-      else if (CM && (CM % 32 == 0)) prefilter<true, true, false, false>(V.tposf() + tb, 32, xf, yf, P.f_dp, 0.f, 0.f, ct, u1, u2);
-      else prefilter<false, true, false, false>(V.tposf() + tb, len, xf, yf, P.f_dp, 0.f, 0.f, ct, u1, u2);
+      else prefilter(V.tposf() + tb, len, xf, yf, P.f_dp, P.f_dp, P.f_dp, ct, u1, u2);
       if (MASKS)
         for (int jj = 0; jj < len; jj++) { B.obs_mask[mrow_t + tb + jj] = 0; B.cover_mask[mrow_t + tb + jj] = 0; }
+#pragma unroll 1
       while (ct) {
         const int jj = __ffs((int)ct) - 1;
         ct &= ct - 1;
@@ -447,20 +376,11 @@ __device__ __forceinline__ void agent_fast(const KParams &P, const UavSimBuffers
   const float k_ex0 = 1.4426950408889634f, k_ex1 = (float)(-1.4426950408889634 / P.two_dp);
   CommAcc A = {0, 0, 0, 0, 0, 0};
   double dup = 0;
-  const int w0 = i & ~31;  // first UAV of this warp (WARP_ENV)
-#pragma unroll
+#pragma unroll 1
   for (int c = 0; c < 4; c++) {
     const int jb = 32 * c;
     uint32_t nbits = 0;
-    if (jb < n) {
-      if (WARP_ENV) {  // n % 32 == 0: full chunks, warp-uniform kind
-        if (jb < w0) nbits = pair_chunk<PAIR_MOVED, true, true, MASKS>(P, B, V, jb, 32, i, xi, yi, xf, yf, far_env, k_ex0, k_ex1, A, dup, mrow_u);
-        else if (jb > w0) nbits = pair_chunk<PAIR_UNMOVED, true, true, MASKS>(P, B, V, jb, 32, i, xi, yi, xf, yf, far_env, k_ex0, k_ex1, A, dup, mrow_u);
-        else nbits = pair_chunk<PAIR_MIXED, true, true, MASKS>(P, B, V, jb, 32, i, xi, yi, xf, yf, far_env, k_ex0, k_ex1, A, dup, mrow_u);
-      } else {
-        nbits = pair_chunk<PAIR_MIXED, false, false, MASKS>(P, B, V, jb, min(32, n - jb), i, xi, yi, xf, yf, far_env, k_ex0, k_ex1, A, dup, mrow_u);
-      }
-    }
+    if (jb < n) nbits = pair_chunk<MASKS>(P, B, V, jb, min(32, n - jb), i, xi, yi, xf, yf, far_env, k_ex0, k_ex1, A, dup, mrow_u);
     O.nb[c] = nbits;
   }
 
@@ -515,16 +435,16 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
       const EnvView V{S.env + (size_t)te * L.stride, L};
       double x = B.tx[gi], y = B.ty[gi], h = B.th[gi];
       double sh, ch;
-      sincos(h, &sh, &ch);
+      sincos_shared(h, &sh, &ch);
       x += P.dtv_t * ch;
       y += P.dtv_t * sh;
-      bool refl = false;
+      // reflection (target.py:52-58); cos/sin of the reflected heading follow from the identities
+      // cos(-h) = cos h, sin(-h) = -sin h, cos(+-pi - h) = -cos h, sin(+-pi - h) = sin h (they feed the observation only)
       if (0 > y || y > P.y_max) {
-        h = -h; refl = true;
+        h = -h; sh = -sh; B.th[gi] = h;
       } else if (x < 0 || x > P.x_max) {
-        h = (h > 0) ? (PI_D - h) : (-PI_D - h); refl = true;
+        h = (h > 0) ? (PI_D - h) : (-PI_D - h); ch = -ch; B.th[gi] = h;
       }
-      if (refl) { sincos(h, &sh, &ch); B.th[gi] = h; }
       B.tx[gi] = x; B.ty[gi] = y;
       V.tpos()[t] = make_double2(x, y);
       // cos(target.h) * target.v_max / self.v_max  (src/agent/uav.py:115-116)
@@ -543,7 +463,7 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
       double x = B.ux[gi], y = B.uy[gi], h = B.uh[gi];
       const int a_old = B.ua[gi], act = B.actions[gi];
       double sh, ch;
-      sincos(h, &sh, &ch);
+      sincos_shared(h, &sh, &ch);
       V.opos()[i] = make_double2(x, y); V.ohd()[i] = make_double2(ch, sh); V.oa()[i] = a_old;
       x += P.dtv_u * ch;
       y += P.dtv_u * sh;
@@ -573,9 +493,7 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
       float *ob = S.obs + (size_t)q * 12;
       const int64_t mrow_t = (ge * n + i) * m, mrow_u = (ge * n + i) * n;
       // row weights differ from 1 only if |x| < 2 and |y| < 2 (|rx|,|ry| <= 1 for any row in range)
-      bool near_origin = fabs(xi) < 2.0 && fabs(yi) < 2.0;
-      // the fast path uses warp-wide intrinsics when the warp lies inside one environment: keep the branch uniform
-      if (WARP_ENV) near_origin = __any_sync(0xffffffffu, near_origin);
+      const bool near_origin = fabs(xi) < 2.0 && fabs(yi) < 2.0;
       if (near_origin) agent_exact<MASKS>(P, B, V, S.tcnt + el * m, i, n, m, ob, mrow_t, mrow_u, &O);
       else agent_fast<CN, CM, WARP_ENV, MASKS>(P, B, V, S.tcnt + el * m, i, n, m, S.far[el] != 0, ob, mrow_t, mrow_u, O);
       if (MASKS) { B.comm_mask[mrow_u + i] = 0; B.nbr_mask[mrow_u + i] = 0; B.dup_mask[mrow_u + i] = 0; }

@@ -129,7 +129,7 @@ extern "C" int uavsim_create(const UavSimParams *p, int64_t n_envs, int64_t env_
 
   // launch geometry of the step kernel: one thread per UAV, nt / n environments per CTA.  Small CTAs keep the
   // phase barriers cheap (the exact pass has data-dependent length); compile-time sizes for the two headline scenarios
-  if (k.n == 64 && k.m == 64) { h->nt = 64; h->step_fn[0] = uavsim_step_kernel<64, 64, false, 64>; h->step_fn[1] = uavsim_step_kernel<64, 64, true, 64>; }
+  if (k.n == 64 && k.m == 64) { h->nt = UAVSIM_NT64; h->step_fn[0] = uavsim_step_kernel<64, 64, false, UAVSIM_NT64>; h->step_fn[1] = uavsim_step_kernel<64, 64, true, UAVSIM_NT64>; }
   else if (k.n == 10 && k.m == 10) { h->nt = 128; h->step_fn[0] = uavsim_step_kernel<10, 10, false, 128>; h->step_fn[1] = uavsim_step_kernel<10, 10, true, 128>; }
   else { h->nt = 128; h->step_fn[0] = uavsim_step_kernel<0, 0, false, 128>; h->step_fn[1] = uavsim_step_kernel<0, 0, true, 128>; }
   int epb = h->nt / p->n_uav;
