@@ -39,6 +39,7 @@ struct KParams {
   double alpha, beta, gamma;
   double tt_hi;               // 2*m_targets            (src/environment.py:207-208)
   double dup_lo;              // -e/2*n_uav             (src/environment.py:209-210)
+  double inv_dp, inv_dc, inv_na, inv_tt_hi, inv_dup_span;  // reciprocals for fp32-bound outputs
   // fp32 prefilter: map centre, validity radius, guarded squared thresholds (thr^2 + fp32 error bound)
   double cx, cy, rmax;
   float f_dp, f_dc, f_2dp, f_dcmv;  // f_dcmv: dc + dt*v_max (old position bounded through the new one)

@@ -108,6 +108,19 @@ struct EnvView {
 // one copy of the fp64 sincos code for both call sites (instruction-fetch footprint)
 __device__ __noinline__ void sincos_shared(double h, double *s, double *c) { sincos(h, s, c); }
 
+// (h + pi) % (2 pi) - pi with Python's float % (uav.py:97).  For h + pi in [-2pi, 4pi) -- always, unless dt * rate
+// exceeds a full turn -- the fmod is one exact subtraction (Sterbenz) or, below zero, the same single addition
+// CPython performs after fmod; otherwise the general routine.
+__device__ __forceinline__ double wrap_heading(double h) {
+  const double TWO_PI = 2 * PI_D;
+  double x = h + PI_D;
+  if (x >= 0.0 && x < TWO_PI) { /* fmod is the identity */ }
+  else if (x >= TWO_PI && x < 2 * TWO_PI) x -= TWO_PI;
+  else if (x < 0.0 && x > -TWO_PI) x += TWO_PI;
+  else x = pymod_pos(x, TWO_PI);
+  return x - PI_D;
+}
+
 // what phase 1 produces for one UAV
 struct AgentOut {
   double tt, dup;         // raw tracking reward / duplicate punishment (before normalisation)
@@ -274,43 +287,44 @@ __device__ __forceinline__ uint32_t pair_chunk(const KParams &P, const UavSimBuf
   if (MASKS)
     for (int jj = 0; jj < len; jj++) { B.comm_mask[mrow_u + jb + jj] = 0; B.nbr_mask[mrow_u + jb + jj] = 0; B.dup_mask[mrow_u + jb + jj] = 0; }
 
-  // (B) exact fp64 evaluation of the candidates only, ascending j like the reference's loops.  Each lane walks
-  // its own bits; the warp runs max-over-lanes iterations.
+  // (B) exact fp64 evaluation of the candidates only.  Each lane walks its own bits (ascending j, like the
+  // reference's loops); the warp runs max-over-lanes trips, so the two lists get two lean loops instead of one
+  // fat one.  Sums over the two lists commute up to fp64 rounding of the (order-dependent) additions.
   const double2 *npos = V.npos(), *nhd = V.nhd(), *opos = V.opos(), *ohd = V.ohd();
-  uint32_t todo = cn | co, nbits = 0;
+  const int *na_ = V.na_(), *oa = V.oa();
+  uint32_t nbits = 0;
 #pragma unroll 1
-  while (todo) {
-    const int jj = __ffs((int)todo) - 1;
-    const uint32_t bit = 1u << jj;
-    todo &= todo - 1;
+  while (cn) {  // partner's NEW position: duplicate term, neighbour bit, and communication if it moved first
+    const int jj = __ffs((int)cn) - 1;
+    cn &= cn - 1;
     const int j = jb + jj;
-    bool hc = false;
-    if (cn & bit) {
-      const double2 np = npos[j];
-      const double dxn = np.x - xi, dyn = np.y - yi;
-      const double d2n = dxn * dxn + dyn * dyn;
-      const bool hd = d2n <= P.s_2dp_le;  // uav.py:225
-      const bool hn = d2n <= P.s_dp_le;   // uav.py:305
-      if (hd) dup += (double)fast_ex2f(fmaf(fast_sqrtf((float)d2n), k_ex1, k_ex0));  // exp((2dp - d)/(2dp))
-      if (hn) nbits |= bit;
-      if (MASKS) { B.nbr_mask[mrow_u + j] = hn; B.dup_mask[mrow_u + j] = hd; }
-      if ((lt & bit) && d2n <= P.s_dc_le) {  // uav.py:135, partner already at its new state
-        const double2 h = nhd[j];
-        A.sx += dxn; A.sy += dyn; A.sc += h.x; A.ss += h.y; A.sa += V.na_()[j]; A.cnt++;
-        hc = true;
-      }
+    const double2 np = npos[j];
+    const double dxn = np.x - xi, dyn = np.y - yi;
+    const double d2n = dxn * dxn + dyn * dyn;
+    const bool hd = d2n <= P.s_2dp_le;  // uav.py:225
+    const bool hn = d2n <= P.s_dp_le;   // uav.py:305
+    const bool hc = (jj < sj) && (d2n <= P.s_dc_le);  // uav.py:135, partner already at its new state
+    if (hd) dup += (double)fast_ex2f(fmaf(fast_sqrtf((float)d2n), k_ex1, k_ex0));  // exp((2dp - d)/(2dp))
+    if (hn) nbits |= 1u << jj;
+    if (hc) {
+      const double2 h = nhd[j];
+      A.sx += dxn; A.sy += dyn; A.sc += h.x; A.ss += h.y; A.sa += na_[j]; A.cnt++;
     }
-    if (co & bit) {
-      const double2 op = opos[j];
-      const double dxo = op.x - xi, dyo = op.y - yi;
-      const double d2o = dxo * dxo + dyo * dyo;
-      if (d2o <= P.s_dc_le) {  // partner still at its old state
-        const double2 h = ohd[j];
-        A.sx += dxo; A.sy += dyo; A.sc += h.x; A.ss += h.y; A.sa += V.oa()[j]; A.cnt++;
-        hc = true;
-      }
+    if (MASKS) { B.nbr_mask[mrow_u + j] = hn; B.dup_mask[mrow_u + j] = hd; if (hc) B.comm_mask[mrow_u + j] = 1; }
+  }
+#pragma unroll 1
+  while (co) {  // partner's OLD position (it moves after i): communication only
+    const int jj = __ffs((int)co) - 1;
+    co &= co - 1;
+    const int j = jb + jj;
+    const double2 op = opos[j];
+    const double dxo = op.x - xi, dyo = op.y - yi;
+    const double d2o = dxo * dxo + dyo * dyo;
+    if (d2o <= P.s_dc_le) {
+      const double2 h = ohd[j];
+      A.sx += dxo; A.sy += dyo; A.sc += h.x; A.ss += h.y; A.sa += oa[j]; A.cnt++;
+      if (MASKS) B.comm_mask[mrow_u + j] = 1;
     }
-    if (MASKS) B.comm_mask[mrow_u + j] = hc;
   }
   return nbits;
 }
@@ -360,11 +374,11 @@ __device__ __forceinline__ void agent_fast(const KParams &P, const UavSimBuffers
     }
     // observation part of the local state (uav.py:176-186; row weights are all 1 here), -1 block when empty
     if (nobs) {
-      const double k = (double)nobs;
-      ob[5] = (float)(ox / P.dp / k);
-      ob[6] = (float)(oy / P.dp / k);
-      ob[7] = (float)((ovx - k * chi) / k);
-      ob[8] = (float)((ovy - k * shi) / k);
+      const double k = (double)nobs, rk = 1.0 / k, rs = rk * P.inv_dp;  // outputs are fp32: reciprocals are exact enough
+      ob[5] = (float)(ox * rs);
+      ob[6] = (float)(oy * rs);
+      ob[7] = (float)((ovx - k * chi) * rk);
+      ob[8] = (float)((ovy - k * shi) * rk);
     } else {
       ob[5] = ob[6] = ob[7] = ob[8] = -1.f;
     }
@@ -386,13 +400,13 @@ __device__ __forceinline__ void agent_fast(const KParams &P, const UavSimBuffers
 
   // ---- communication part of the local state (uav.py:162-172)
   if (A.cnt) {
-    const double k = (double)A.cnt;
+    const double k = (double)A.cnt, rk = 1.0 / k, rs = rk * P.inv_dc;
     const int ai = V.na_()[i];
-    ob[0] = (float)(A.sx / P.dc / k);
-    ob[1] = (float)(A.sy / P.dc / k);
-    ob[2] = (float)((A.sc - k * chi) / k);
-    ob[3] = (float)((A.ss - k * shi) / k);
-    ob[4] = (float)((double)(A.sa - A.cnt * ai) / (double)P.na / k);
+    ob[0] = (float)(A.sx * rs);
+    ob[1] = (float)(A.sy * rs);
+    ob[2] = (float)((A.sc - k * chi) * rk);
+    ob[3] = (float)((A.ss - k * shi) * rk);
+    ob[4] = (float)((double)(A.sa - A.cnt * ai) * P.inv_na * rk);
   } else {
     ob[0] = ob[1] = ob[2] = ob[3] = ob[4] = -1.f;
   }
@@ -468,7 +482,7 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
       x += P.dtv_u * ch;
       y += P.dtv_u * sh;
       h += S.dth[3 * act];
-      h = pymod_pos(h + PI_D, 2 * PI_D) - PI_D;
+      h = wrap_heading(h);
       // cos/sin of the new heading by angle addition (|error| ~ 3e-16; they only feed the observation).
       // The next step re-evaluates sincos from the stored heading, so the trajectory is unaffected.
       const double cd = S.dth[3 * act + 1], sd = S.dth[3 * act + 2];
@@ -497,21 +511,21 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
       if (near_origin) agent_exact<MASKS>(P, B, V, S.tcnt + el * m, i, n, m, ob, mrow_t, mrow_u, &O);
       else agent_fast<CN, CM, WARP_ENV, MASKS>(P, B, V, S.tcnt + el * m, i, n, m, S.far[el] != 0, ob, mrow_t, mrow_u, O);
       if (MASKS) { B.comm_mask[mrow_u + i] = 0; B.nbr_mask[mrow_u + i] = 0; B.dup_mask[mrow_u + i] = 0; }
-      ob[9] = (float)(xi / P.dc);
-      ob[10] = (float)(yi / P.dc);
-      ob[11] = (float)((double)ai / (double)P.na);
+      ob[9] = (float)(xi * P.inv_dc);
+      ob[10] = (float)(yi * P.inv_dc);
+      ob[11] = (float)((double)ai * P.inv_na);
 
       // boundary punishment (uav.py:231-250)
       const double dbdr = fmin(fmin(xi - 0, P.x_max - xi), fmin(yi - 0, P.y_max - yi));
       double bp;
       if (0 <= xi && xi <= P.x_max && 0 <= yi && yi <= P.y_max)
-        bp = (dbdr < P.dp) ? (-0.5 * (P.dp - dbdr) / P.dp) : 0.0;
+        bp = (dbdr < P.dp) ? (-0.5 * (P.dp - dbdr) * P.inv_dp) : 0.0;
       else
         bp = -0.5;
       // normalise + weights (environment.py:206-220)
-      ttn = clipnorm_0(O.tt, P.tt_hi);
-      dupn = clipnorm_m1(O.dup, P.dup_lo);
-      bpn = clipnorm_m1(bp, -0.5);
+      ttn = fmin(fmax(O.tt, 0.0), P.tt_hi) * P.inv_tt_hi;                      // choice 0: (v - 0)/(2m - 0)
+      dupn = (fmin(fmax(O.dup, P.dup_lo), 0.0) - P.dup_lo) * P.inv_dup_span - 1.0;  // choice -1: (v - lo)/(0 - lo) - 1
+      bpn = (fmin(fmax(bp, -0.5), 0.0) + 0.5) * 2.0 - 1.0;
       raw = P.alpha * ttn + P.beta * bpn + P.gamma * dupn;
       S.raw[q] = raw;
     }

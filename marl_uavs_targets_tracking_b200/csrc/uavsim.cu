@@ -104,6 +104,8 @@ extern "C" int uavsim_create(const UavSimParams *p, int64_t n_envs, int64_t env_
   k.alpha = p->alpha; k.beta = p->beta; k.gamma = p->gamma;
   k.tt_hi = (double)(2 * p->m_targets);
   k.dup_lo = -2.718281828459045 / 2 * p->n_uav;
+  k.inv_dp = 1.0 / p->dp; k.inv_dc = 1.0 / p->dc; k.inv_na = 1.0 / (double)p->na;
+  k.inv_tt_hi = 1.0 / k.tt_hi; k.inv_dup_span = 1.0 / (0.0 - k.dup_lo);
   // fp32 prefilter (step_kernel.cuh): coordinates relative to the map centre, valid while every entity is within
   // rmax of it; the guard band bounds the fp32 error of the squared distance so no true hit is ever dropped
   k.cx = p->x_max / 2; k.cy = p->y_max / 2;
