@@ -127,7 +127,7 @@ def cpu_oracle_rate(n, m, method, budget_s, threads, seed=0):
     mode = {"MAAC": 0, "MAAC-G": 1, "MAAC-R": 2}[method]
     pmi = oracle_pmi_from_module(make_pmi(torch)) if method == "MAAC-R" else None
     orc = Oracle()
-    E = max(threads * 4, 8)
+    E = max(threads * 16, 32)
     st = reset_reference(seed, E, n, m, 12, 2000, 2000)
     st = {k: np.ascontiguousarray(v) for k, v in st.items()}
     rng = np.random.RandomState(seed)
@@ -135,7 +135,7 @@ def cpu_oracle_rate(n, m, method, budget_s, threads, seed=0):
     t0 = time.perf_counter()
     orc.step_batch(P, mode, float(cfg["cooperative"]), pmi, st, acts, nthreads=threads, want_tracker=False)
     one = max(time.perf_counter() - t0, 1e-4)
-    steps = int(max(3, min(2000, budget_s / one)))
+    steps = int(max(3, min(100000, budget_s / one)))
     t0 = time.perf_counter()
     for _ in range(steps):
         acts = rng.randint(0, 12, size=(E, n)).astype(np.int32)
