@@ -139,6 +139,10 @@ int uavsim_set_reward_weights(uavsim_t *h, double alpha, double beta, double gam
 /* pmi argument of Environment.step / PMINetwork.inference (src/models/PMINet.py:64-72). */
 int uavsim_set_pmi_weights(uavsim_t *h, const UavSimPmiWeights *w, void *stream);
 
+/* Which kernel evaluates the PMI MLP: 0 = automatic (tensor cores when hidden == 128 and the neighbour lists fit),
+ * 1 = fp32 CUDA cores, 2 = tcgen05 tensor cores with 3xTF32 split operands (error if unsupported). */
+int uavsim_set_pmi_path(uavsim_t *h, int path);
+
 /* Episode statistics accumulated by uavsim_step since the last reset (src/train.py:181-192):
  * out[0..3] = sums of rewards / tracking / boundary / duplicate over env-steps and UAVs,
  * out[4] = sum of covered_targets over env-steps, out[5] = max covered_targets,

@@ -54,6 +54,8 @@ struct PmiDev {
 typedef void (*StepKernelFn)(const KParams, const UavSimBuffers, const double *, int64_t, int64_t, int, int, double,
                              int, double *);
 
+struct PmiTcDev;
+
 struct uavsim {
   UavSimParams hp;
   KParams kp;
@@ -74,6 +76,11 @@ struct uavsim {
   PmiDev pmi;
   float *d_pmi_blob;
   int pmi_g, pmi_pmax, pmi_tm, pmi_grid_max;
+  // tensor-core path (H = 128): fc1 pre-split into UMMA tiles
+  bool has_tc;
+  int pmi_path;        // 0 auto, 1 CUDA cores, 2 tensor cores
+  float *d_tc_tiles;   // [12][2][128*32]
+  int tc_g;
   size_t smem_pmi;
   // host-buffer pipeline
   cudaStream_t s_in, s_comp, s_out;

@@ -1,0 +1,321 @@
+// pmi_tc_kernel.cuh -- PMI reciprocal reward on the 5th-generation tensor cores (tcgen05, sm_100a), H = 128.
+//
+// Same contract as uavsim_pmi_kernel (pmi_kernel.cuh): for every ordered neighbour pair (i, j) of an environment
+// the folded PMINetwork (src/models/PMINet.py:41-62) maps la_i * la_j (12 values) to a logit; a float32 softmax
+// over each UAV's neighbours mixes their raw rewards (src/agent/uav.py:262-291).
+//
+// Mapping.  One CTA (128 threads) per SM, persistent over groups of environments.  Pair rows are processed in
+// tiles of 128 (thread r owns row r = TMEM lane r).  The 384 -> 128 layer is a [128 x 384] x [384 x 128] GEMM per
+// tile, issued by one thread as tcgen05.mma.kind::tf32 (M = 128, N = 128, K = 8) with the fp32 accumulator in
+// tensor memory.  Precision: single-pass TF32 (10-bit mantissa) misses the 1e-5 bar, so
+// both operands are split x = hi + lo (hi = tf32(x), lo = tf32(x - hi)) and every K-slice runs three MMAs
+// hi*hi + lo*hi + hi*lo -- fp32-class products, fp32 accumulation.
+//   A (activations after layer 0): computed on CUDA cores per 32-unit K-chunk (block-diagonal 12 -> 384, <= 5 FMAs
+//     per unit), split, and written straight into the canonical K-major no-swizzle UMMA layout
+//     byte(r, k) = (k/4)*2048 + (r/8)*128 + (r%8)*16 + (k%4)*4   (8x16-byte core matrices, LBO 2048, SBO 128)
+//     -- thread r writes one 16-byte vector per 4 units, consecutive threads consecutive vectors (no bank conflicts).
+//   B (fc1 weights): pre-split and pre-arranged on the host in the same layout, one 32 KB block (hi | lo) per
+//     K-chunk, fetched with one cp.async.bulk (TMA engine, mbarrier complete_tx) per chunk.
+//   Two stages: the MMAs of chunk c run while the threads compute chunk c+1; tcgen05.commit releases a stage.
+// Epilogue: tcgen05.ld (32 lanes x 32 columns per warp and instruction) -> bias + ReLU -> dot with fc2 in the owning
+// thread (a thread holds a full row, no shuffles) -> logit in shared memory; then softmax + mix per UAV.
+#pragma once
+#include "common.cuh"
+
+#define TC_NT 128            // threads per CTA (4 warps = the 4 TMEM lane quarters)
+#define TC_H 128
+#define TC_H3 384
+#define TC_KC 32             // hidden units per K-chunk
+#define TC_NCHUNK (TC_H3 / TC_KC)
+#define TC_TILE_BYTES 16384  // one 128 x 32 fp32 operand tile
+#define TC_AMAX 512          // UAVs per environment group
+#define TC_PMAX 8192         // neighbour pairs per environment group
+
+// instruction descriptor: D = F32, A = B = TF32, K-major both, N = 128 (>>3 at bit 17), M = 128 (>>4 at bit 24)
+#define TC_IDESC ((1u << 4) | (2u << 7) | (2u << 10) | ((TC_H >> 3) << 17) | ((128u >> 4) << 24))
+
+struct TcSmem {  // byte offsets inside dynamic shared memory (base is 1024-byte aligned)
+  static constexpr uint32_t stage = 0;                                   // 2 x (A_hi, A_lo, B_hi, B_lo)
+  static constexpr uint32_t obs = 2 * 4 * TC_TILE_BYTES;                 // float [AMAX*12]
+  static constexpr uint32_t raw = obs + TC_AMAX * 12 * 4;                // double [AMAX]
+  static constexpr uint32_t nbr = raw + TC_AMAX * 8;                     // uint64 [AMAX*2]
+  static constexpr uint32_t off = nbr + TC_AMAX * 16;                    // uint32 [AMAX+4]
+  static constexpr uint32_t logit = off + (TC_AMAX + 4) * 4;             // float [PMAX]
+  static constexpr uint32_t w0 = logit + TC_PMAX * 4;                    // float [384*5]
+  static constexpr uint32_t b0 = w0 + TC_H3 * 5 * 4;                     // float [384]
+  static constexpr uint32_t b1 = b0 + TC_H3 * 4;                         // float [128]
+  static constexpr uint32_t w2 = b1 + TC_H * 4;                          // float [128]
+  static constexpr uint32_t red = w2 + TC_H * 4;                         // double [64]
+  static constexpr uint32_t bar = red + 64 * 8;                          // 5 mbarriers + tmem pointer
+  static constexpr uint32_t total = bar + 64;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait: a barrier that never completes (a descriptor bug) traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; spin++) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  // K-major, no swizzle: start address, LBO = 2048 B (between the two 16-byte K halves of an MMA),
+  // SBO = 128 B (between 8-row groups), descriptor version 1 (Blackwell)
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(2048u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) |
+         (1ull << 46);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(TC_IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float tf32_rna(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+  uint32_t *u = reinterpret_cast<uint32_t *>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+        "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+        "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct PmiTcDev {
+  const float *w0, *b0, *b1, *w2;  // [384*5] [384] [128] [128] folded fp32
+  const float *w1_tiles;           // [12][2][128 x 32] fc1 pre-split (hi | lo) in the UMMA layout
+  float b2;
+};
+
+__global__ void __launch_bounds__(TC_NT, 1)
+uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, int64_t env_begin, int64_t env_count,
+                     int G, double coop, double *__restrict__ stats_partial) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int n = P.n, tid = threadIdx.x, warp = tid >> 5;
+  float *s_obs = reinterpret_cast<float *>(smem + TcSmem::obs);
+  double *s_raw = reinterpret_cast<double *>(smem + TcSmem::raw);
+  uint64_t *s_nbr = reinterpret_cast<uint64_t *>(smem + TcSmem::nbr);
+  uint32_t *s_off = reinterpret_cast<uint32_t *>(smem + TcSmem::off);
+  float *s_logit = reinterpret_cast<float *>(smem + TcSmem::logit);
+  float *s_w0 = reinterpret_cast<float *>(smem + TcSmem::w0);
+  float *s_b0 = reinterpret_cast<float *>(smem + TcSmem::b0);
+  float *s_b1 = reinterpret_cast<float *>(smem + TcSmem::b1);
+  float *s_w2 = reinterpret_cast<float *>(smem + TcSmem::w2);
+  double *s_red = reinterpret_cast<double *>(smem + TcSmem::red);
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + TcSmem::bar + 48);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_full0 = sbase + TcSmem::bar, bar_free0 = bar_full0 + 16, bar_acc = bar_full0 + 32;
+
+  for (int k = tid; k < TC_H3 * 5; k += TC_NT) s_w0[k] = W.w0[k];
+  for (int k = tid; k < TC_H3; k += TC_NT) s_b0[k] = W.b0[k];
+  for (int k = tid; k < TC_H; k += TC_NT) { s_b1[k] = W.b1[k]; s_w2[k] = W.w2[k]; }
+  if (tid == 0) {
+    mbar_init(bar_full0, 1); mbar_init(bar_full0 + 8, 1);
+    mbar_init(bar_free0, 1); mbar_init(bar_free0 + 8, 1);
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {  // tensor memory: 128 fp32 accumulator columns, allocated by one warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *s_tmem;
+
+  uint32_t use0 = 0, use1 = 0;  // how often each stage has been filled (phase bookkeeping)
+  uint32_t tiles_done = 0;
+  const int64_t ngroups = (env_count + G - 1) / G;
+  double st_r = 0;
+
+  for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const int64_t e0 = env_begin + grp * G;
+    const int ne = (int)min((int64_t)G, env_begin + env_count - e0);
+    const int A = ne * n;  // UAVs in this group (<= TC_AMAX)
+    __syncthreads();
+    for (int k = tid; k < A * 12; k += TC_NT) s_obs[k] = B.obs[e0 * n * 12 + k];
+    for (int a = tid; a < A; a += TC_NT) {
+      s_raw[a] = B.raw[e0 * n + a];
+      const uint64_t n0 = B.nbr_bits[(e0 * n + a) * 2], n1 = B.nbr_bits[(e0 * n + a) * 2 + 1];
+      s_nbr[2 * a] = n0; s_nbr[2 * a + 1] = n1;
+      s_off[a + 1] = __popcll(n0) + __popcll(n1);
+    }
+    __syncthreads();
+    if (warp == 0) {  // exclusive scan of the neighbour counts (A <= 512): 16 per lane + warp scan
+      const int per = (A + 31) / 32, lo = (tid & 31) * per;
+      uint32_t sum = 0;
+      for (int k = 0; k < per; k++) if (lo + k < A) sum += s_off[lo + k + 1];
+      uint32_t inc = sum;
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if ((tid & 31) >= o) inc += v; }
+      uint32_t run = inc - sum;
+      if (tid == 0) s_off[0] = 0;
+      for (int k = 0; k < per; k++) if (lo + k < A) { run += s_off[lo + k + 1]; s_off[lo + k + 1] = run; }
+    }
+    __syncthreads();
+    const int npairs = (int)s_off[A];
+
+    for (int p0 = 0; p0 < npairs; p0 += 128) {
+      // ---- this thread's pair row: flat index -> (UAV a, its k-th neighbour b), x = la_a * la_b (uav.py:280-281)
+      float x[12];
+      const int p = p0 + tid;
+      if (p < npairs) {
+        int lo = 0, hi = A;  // largest a with off[a] <= p
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= (uint32_t)p) lo = mid; else hi = mid; }
+        const int a = lo;
+        int k = p - (int)s_off[a];
+        uint64_t w = s_nbr[2 * a];
+        int base = (a / n) * n;
+        const int c0 = __popcll(w);
+        if (k >= c0) { k -= c0; w = s_nbr[2 * a + 1]; base += 64; }
+        for (int t = 0; t < k; t++) w &= w - 1;
+        const int b = base + __ffsll((long long)w) - 1;
+#pragma unroll
+        for (int q = 0; q < 12; q++) x[q] = s_obs[a * 12 + q] * s_obs[b * 12 + q];
+      } else {
+#pragma unroll
+        for (int q = 0; q < 12; q++) x[q] = 0.f;
+      }
+
+      // ---- layer 1 GEMM, 12 K-chunks of 32 hidden units through the two stages.  The three input branches
+      //      (communication 5, observation 4, boundary/state 3 inputs; PMINet.py:45-58, BN folded) are unrolled
+      //      so the row stays in registers; each branch covers 4 chunks.
+      auto run_chunk = [&](const int c, const float *xin, const int dim) {
+        const int s = c & 1;
+        const uint32_t stage = sbase + TcSmem::stage + (uint32_t)s * 4u * TC_TILE_BYTES;
+        const uint32_t use = s ? use1 : use0;
+        if (use > 0) mbar_wait(bar_free0 + 8 * s, (use - 1) & 1);  // MMAs that read this stage have completed
+        if (tid == 0) {
+          mbar_expect_tx(bar_full0 + 8 * s, 2 * TC_TILE_BYTES);
+          bulk_g2s(stage + 2 * TC_TILE_BYTES, W.w1_tiles + (size_t)c * (2 * TC_TILE_BYTES / 4), 2 * TC_TILE_BYTES, bar_full0 + 8 * s);
+        }
+        unsigned char *a_hi = smem + TcSmem::stage + (size_t)s * 4 * TC_TILE_BYTES, *a_lo = a_hi + TC_TILE_BYTES;
+#pragma unroll 2
+        for (int g = 0; g < TC_KC / 4; g++) {
+          float hv[4], lv[4];
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const int u = c * TC_KC + g * 4 + e;
+            const float *wr = s_w0 + u * 5;
+            float acc = s_b0[u];
+#pragma unroll
+            for (int q = 0; q < 5; q++) if (q < dim) acc = fmaf(wr[q], xin[q], acc);
+            acc = fmaxf(acc, 0.f);
+            hv[e] = tf32_rna(acc);
+            lv[e] = tf32_rna(acc - hv[e]);
+          }
+          *reinterpret_cast<float4 *>(a_hi + g * 2048 + tid * 16) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+          *reinterpret_cast<float4 *>(a_lo + g * 2048 + tid * 16) = make_float4(lv[0], lv[1], lv[2], lv[3]);
+        }
+        if (s) use1 = use + 1; else use0 = use + 1;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+          mbar_wait(bar_full0 + 8 * s, use & 1);  // fc1 chunk has landed
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t ah = stage, al = stage + TC_TILE_BYTES, bh = stage + 2 * TC_TILE_BYTES, bl = stage + 3 * TC_TILE_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < TC_KC / 8; ks++) {  // one MMA consumes K = 8 = two 16-byte core-matrix columns
+            const uint32_t o = (uint32_t)ks * 2u * 2048u;
+            umma_tf32(tmem_d, umma_desc(ah + o), umma_desc(bh + o), (c | ks) ? 1u : 0u);
+            umma_tf32(tmem_d, umma_desc(al + o), umma_desc(bh + o), 1u);
+            umma_tf32(tmem_d, umma_desc(ah + o), umma_desc(bl + o), 1u);
+          }
+          umma_commit(bar_free0 + 8 * s);                  // stage reusable when these MMAs are done
+          if (c == TC_NCHUNK - 1) umma_commit(bar_acc);    // accumulator complete
+        }
+      };
+#pragma unroll 1
+      for (int cc = 0; cc < 4; cc++) run_chunk(cc, x, 5);
+#pragma unroll 1
+      for (int cc = 4; cc < 8; cc++) run_chunk(cc, x + 5, 4);
+#pragma unroll 1
+      for (int cc = 8; cc < 12; cc++) run_chunk(cc, x + 9, 3);
+
+      // ---- epilogue: bias + ReLU + fc2 (PMINet.py:59-62), one accumulator row per thread
+      mbar_wait(bar_acc, tiles_done & 1);
+      tiles_done++;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float part = 0.f;
+#pragma unroll 1
+      for (int cb = 0; cb < TC_H; cb += 32) {
+        float v[32];
+        tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb, v);
+#pragma unroll
+        for (int k = 0; k < 32; k++) part = fmaf(s_w2[cb + k], fmaxf(v[k] + s_b1[cb + k], 0.f), part);
+      }
+      if (p < npairs) s_logit[p] = part + W.b2;
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();  // every row has left tensor memory before the next tile overwrites it
+    }
+    __syncthreads();
+
+    // ---- softmax over each UAV's neighbours (scipy.special.softmax on float32) and the mix (uav.py:284-290)
+    for (int a = tid; a < A; a += TC_NT) {
+      const uint32_t lo = s_off[a], hi = s_off[a + 1];
+      const double raw = s_raw[a];
+      double r;
+      if (hi > lo) {
+        float mx = s_logit[lo];
+        for (uint32_t q = lo + 1; q < hi; q++) mx = fmaxf(mx, s_logit[q]);
+        float ssum = 0.f;
+        for (uint32_t q = lo; q < hi; q++) ssum += expf(s_logit[q] - mx);
+        double acc = 0;
+        uint32_t q = lo;
+        const int base = (a / n) * n;
+        for (int half = 0; half < 2; half++) {
+          uint64_t w = s_nbr[2 * a + half];
+          while (w) {
+            const int j = __ffsll((long long)w) - 1;
+            w &= w - 1;
+            const float wgt = expf(s_logit[q] - mx) / ssum;
+            acc += s_raw[base + 64 * half + j] * (double)wgt;
+            q++;
+          }
+        }
+        r = (1 - coop) * raw + coop * acc;
+      } else {
+        r = (1 - coop) * raw;
+      }
+      r = fmin(fmax(r, -1.0), 1.0);
+      B.rew4[e0 * n + a] = (float)r;
+      st_r += r;
+    }
+  }
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(128u) : "memory");
+  block_stats_commit(s_red, stats_partial + (size_t)blockIdx.x * STAT_W, st_r, 0, 0, 0, 0, 0, 0, TC_NT);
+}

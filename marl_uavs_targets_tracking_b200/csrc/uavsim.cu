@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "step_kernel.cuh"
 #include "pmi_kernel.cuh"
+#include "pmi_tc_kernel.cuh"
 #include "aux_kernels.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -175,7 +176,7 @@ extern "C" int uavsim_destroy(uavsim_t *h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaFree(h->d_dth); cudaFree(h->d_stats); cudaFree(h->d_stats8); cudaFreeHost(h->h_stats8);
-  cudaFree(h->d_pmi_blob);
+  cudaFree(h->d_pmi_blob); cudaFree(h->d_tc_tiles);
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_comp) cudaStreamDestroy(h->s_comp);
   if (h->s_out) cudaStreamDestroy(h->s_out);
@@ -311,7 +312,37 @@ static int pmi_launch_t(uavsim_t *h, int64_t e0, int64_t cnt, double coop, cudaS
   return 0;
 }
 
+// round to TF32 like cvt.rna.tf32.f32 (nearest, ties away from zero): keep 10 mantissa bits
+static float host_tf32_rna(float v) {
+  uint32_t b;
+  memcpy(&b, &v, 4);
+  if ((b & 0x7f800000u) != 0x7f800000u) b = (b + 0x1000u) & 0xffffe000u;
+  memcpy(&v, &b, 4);
+  return v;
+}
+
+static bool pmi_use_tensor(const uavsim_t *h) {
+  if (!h->has_tc || h->pmi_path == 1) return false;
+  const int n = h->kp.n;
+  return n * (n - 1) <= TC_PMAX && n <= TC_AMAX;
+}
+
+static int pmi_tc_launch(uavsim_t *h, int64_t e0, int64_t cnt, double coop, cudaStream_t st) {
+  PmiTcDev W;
+  W.w0 = h->pmi.w0; W.b0 = h->pmi.b0; W.b1 = h->pmi.b1; W.w2 = h->pmi.w2; W.b2 = h->pmi.b2;
+  W.w1_tiles = h->d_tc_tiles;
+  const int64_t ngroups = (cnt + h->tc_g - 1) / h->tc_g;
+  int grid = (int)(ngroups < h->sm_count ? ngroups : h->sm_count);
+  if (grid > h->stat_slots) grid = h->stat_slots;
+  uavsim_pmi_tc_kernel<<<grid, TC_NT, TcSmem::total, st>>>(h->kp, h->buf, W, e0, cnt, h->tc_g, coop,
+                                                          h->d_stats + (size_t)h->stat_slots * STAT_W);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
 static int pmi_launch(uavsim_t *h, int64_t e0, int64_t cnt, double coop, cudaStream_t st, bool configure_only) {
+  if (!configure_only && pmi_use_tensor(h)) return pmi_tc_launch(h, e0, cnt, coop, st);
   switch (h->pmi.H) {
     case 32: return pmi_launch_t<2, 64>(h, e0, cnt, coop, st, configure_only);
     case 64: return pmi_launch_t<4, 64>(h, e0, cnt, coop, st, configure_only);
@@ -320,6 +351,16 @@ static int pmi_launch(uavsim_t *h, int64_t e0, int64_t cnt, double coop, cudaStr
   }
   SET_ERR("PMI hidden size %d not supported (32, 64, 128, 256)", h->pmi.H);
   return UAVSIM_ERR_UNSUPPORTED;
+}
+
+extern "C" int uavsim_set_pmi_path(uavsim_t *h, int path) {
+  if (!h || path < 0 || path > 2) { SET_ERR("uavsim_set_pmi_path: bad argument"); return UAVSIM_ERR_ARG; }
+  if (path == 2 && h->has_pmi && !pmi_use_tensor(h) && !(h->has_tc && h->pmi_path == 1)) {
+    SET_ERR("uavsim_set_pmi_path: the tensor-core path needs hidden = 128 and n_uav*(n_uav-1) <= %d", TC_PMAX);
+    return UAVSIM_ERR_UNSUPPORTED;
+  }
+  h->pmi_path = path;
+  return 0;
 }
 
 extern "C" int uavsim_set_pmi_weights(uavsim_t *h, const UavSimPmiWeights *w, void *stream) {
@@ -355,6 +396,34 @@ extern "C" int uavsim_set_pmi_weights(uavsim_t *h, const UavSimPmiWeights *w, vo
   if (rc) return rc;
   rc = pmi_launch(h, 0, 0, 0.0, st, true);
   if (rc) return rc;
+  h->has_tc = false;
+  if (H == TC_H) {
+    // tensor-core path: fc1 split hi/lo (TF32) and laid out as the K-major UMMA tiles the kernel bulk-copies:
+    // chunk c, part {hi, lo}, element (unit o, input k) at float (k/4)*512 + o*4 + (k%4)
+    const size_t tile = TC_TILE_BYTES / 4, total_t = (size_t)TC_NCHUNK * 2 * tile;
+    float *tiles = (float *)malloc(total_t * sizeof(float));
+    for (int c = 0; c < TC_NCHUNK; c++)
+      for (int o = 0; o < TC_H; o++)
+        for (int kk = 0; kk < TC_KC; kk++) {
+          const float v = w->w1[(size_t)o * TC_H3 + c * TC_KC + kk];
+          const float hi = host_tf32_rna(v), lo = host_tf32_rna(v - hi);
+          const size_t e = (size_t)(kk / 4) * 512 + (size_t)o * 4 + (kk % 4);
+          tiles[((size_t)c * 2 + 0) * tile + e] = hi;
+          tiles[((size_t)c * 2 + 1) * tile + e] = lo;
+        }
+    if (!h->d_tc_tiles) CUDA_TRY(cudaMalloc(&h->d_tc_tiles, total_t * sizeof(float)));
+    CUDA_TRY(cudaMemcpyAsync(h->d_tc_tiles, tiles, total_t * sizeof(float), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    free(tiles);
+    rc = raise_dynamic_smem((const void *)uavsim_pmi_tc_kernel, h->device, TcSmem::total);
+    if (rc) return rc;
+    const int n = h->kp.n, per_env = n * (n - 1) > 0 ? n * (n - 1) : 1;
+    int G = TC_AMAX / n;
+    if (G > TC_PMAX / per_env) G = TC_PMAX / per_env;
+    if ((int64_t)G > h->E) G = (int)h->E;
+    h->tc_g = G < 1 ? 1 : G;
+    h->has_tc = true;
+  }
   h->has_pmi = true;
   return 0;
 }

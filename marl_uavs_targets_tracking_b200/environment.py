@@ -216,6 +216,14 @@ class BatchedEnvironment:
         self._ensure_pmi_scratch()
         with torch.cuda.device(self.device):
             _cabi.check(self._lib.uavsim_set_pmi_weights(self._h, C.byref(w), self._stream()), "uavsim_set_pmi_weights")
+        if getattr(self, "_pmi_path", 0):
+            _cabi.check(self._lib.uavsim_set_pmi_path(self._h, self._pmi_path), "uavsim_set_pmi_path")
+
+    def set_pmi_path(self, path):
+        """0 = automatic, 1 = fp32 CUDA cores, 2 = tcgen05 tensor cores (3xTF32)."""
+        self._pmi_path = int(path)
+        if self._h is not None:
+            _cabi.check(self._lib.uavsim_set_pmi_path(self._h, self._pmi_path), "uavsim_set_pmi_path")
 
     def _sync_weights(self, config):
         u = config.get("uav", {})
