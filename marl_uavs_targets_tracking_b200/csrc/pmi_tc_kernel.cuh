@@ -4,8 +4,9 @@
 // the folded PMINetwork (src/models/PMINet.py:41-62) maps la_i * la_j (12 values) to a logit; a float32 softmax
 // over each UAV's neighbours mixes their raw rewards (src/agent/uav.py:262-291).
 //
-// Mapping.  One CTA (128 threads) per SM, persistent over groups of environments.  Pair rows are processed in
-// tiles of 128 (thread r owns row r = TMEM lane r).  The 384 -> 128 layer is a [128 x 384] x [384 x 128] GEMM per
+// Mapping.  One CTA (256 threads) per SM, persistent over groups of environments.  Pair rows are processed in
+// tiles of 128 (threads r and r + 128 share row r = TMEM lane r: each computes half of every layer-0 chunk and
+// half of the epilogue columns).  The 384 -> 128 layer is a [128 x 384] x [384 x 128] GEMM per
 // tile, issued by one thread as tcgen05.mma.kind::tf32 (M = 128, N = 128, K = 8) with the fp32 accumulator in
 // tensor memory.  Precision: single-pass TF32 (10-bit mantissa) misses the 1e-5 bar, so
 // both operands are split x = hi + lo (hi = tf32(x), lo = tf32(x - hi)) and every K-slice runs three MMAs
@@ -22,7 +23,7 @@
 #pragma once
 #include "common.cuh"
 
-#define TC_NT 128            // threads per CTA (4 warps = the 4 TMEM lane quarters)
+#define TC_NT 256            // threads per CTA: 2 threads per pair row; warps w and w+4 share a TMEM lane quarter
 #define TC_H 128
 #define TC_H3 384
 #define TC_KC 32             // hidden units per K-chunk
@@ -41,9 +42,9 @@ struct TcSmem {  // byte offsets inside dynamic shared memory (base is 1024-byte
   static constexpr uint32_t nbr = raw + TC_AMAX * 8;                     // uint64 [AMAX*2]
   static constexpr uint32_t off = nbr + TC_AMAX * 16;                    // uint32 [AMAX+4]
   static constexpr uint32_t logit = off + (TC_AMAX + 4) * 4;             // float [PMAX]
-  static constexpr uint32_t w0 = logit + TC_PMAX * 4;                    // float [384*5]
-  static constexpr uint32_t b0 = w0 + TC_H3 * 5 * 4;                     // float [384]
-  static constexpr uint32_t b1 = b0 + TC_H3 * 4;                         // float [128]
+  static constexpr uint32_t w0 = logit + TC_PMAX * 4;                    // float [384*8]: bias, 5 weights, 2 pad per unit
+  static constexpr uint32_t part = w0 + TC_H3 * 8 * 4;                   // float [128] partial fc2 dots of the upper half
+  static constexpr uint32_t b1 = part + 128 * 4;                         // float [128]
   static constexpr uint32_t w2 = b1 + TC_H * 4;                          // float [128]
   static constexpr uint32_t red = w2 + TC_H * 4;                         // double [64]
   static constexpr uint32_t bar = red + 64 * 8;                          // 5 mbarriers + tmem pointer
@@ -123,14 +124,14 @@ __global__ void __launch_bounds__(TC_NT, 1)
 uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, int64_t env_begin, int64_t env_count,
                      int G, double coop, double *__restrict__ stats_partial) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  const int n = P.n, tid = threadIdx.x, warp = tid >> 5;
+  const int n = P.n, tid = threadIdx.x, warp = tid >> 5, row = tid & 127, half = tid >> 7;
   float *s_obs = reinterpret_cast<float *>(smem + TcSmem::obs);
   double *s_raw = reinterpret_cast<double *>(smem + TcSmem::raw);
   uint64_t *s_nbr = reinterpret_cast<uint64_t *>(smem + TcSmem::nbr);
   uint32_t *s_off = reinterpret_cast<uint32_t *>(smem + TcSmem::off);
   float *s_logit = reinterpret_cast<float *>(smem + TcSmem::logit);
   float *s_w0 = reinterpret_cast<float *>(smem + TcSmem::w0);
-  float *s_b0 = reinterpret_cast<float *>(smem + TcSmem::b0);
+  float *s_part = reinterpret_cast<float *>(smem + TcSmem::part);
   float *s_b1 = reinterpret_cast<float *>(smem + TcSmem::b1);
   float *s_w2 = reinterpret_cast<float *>(smem + TcSmem::w2);
   double *s_red = reinterpret_cast<double *>(smem + TcSmem::red);
@@ -138,8 +139,10 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_full0 = sbase + TcSmem::bar, bar_free0 = bar_full0 + 16, bar_acc = bar_full0 + 32;
 
-  for (int k = tid; k < TC_H3 * 5; k += TC_NT) s_w0[k] = W.w0[k];
-  for (int k = tid; k < TC_H3; k += TC_NT) s_b0[k] = W.b0[k];
+  for (int k = tid; k < TC_H3 * 8; k += TC_NT) {  // per unit: {bias, w0..w4, 0, 0} -> two 128-bit broadcast loads
+    const int u = k >> 3, e = k & 7;
+    s_w0[k] = (e == 0) ? W.b0[u] : (e <= 5 ? W.w0[u * 5 + e - 1] : 0.f);
+  }
   for (int k = tid; k < TC_H; k += TC_NT) { s_b1[k] = W.b1[k]; s_w2[k] = W.w2[k]; }
   if (tid == 0) {
     mbar_init(bar_full0, 1); mbar_init(bar_full0 + 8, 1);
@@ -190,7 +193,7 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
     for (int p0 = 0; p0 < npairs; p0 += 128) {
       // ---- this thread's pair row: flat index -> (UAV a, its k-th neighbour b), x = la_a * la_b (uav.py:280-281)
       float x[12];
-      const int p = p0 + tid;
+      const int p = p0 + row;
       if (p < npairs) {
         int lo = 0, hi = A;  // largest a with off[a] <= p
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= (uint32_t)p) lo = mid; else hi = mid; }
@@ -223,21 +226,25 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
         }
         unsigned char *a_hi = smem + TcSmem::stage + (size_t)s * 4 * TC_TILE_BYTES, *a_lo = a_hi + TC_TILE_BYTES;
 #pragma unroll 2
-        for (int g = 0; g < TC_KC / 4; g++) {
+        for (int g = half * 4; g < half * 4 + 4; g++) {  // this thread's half of the chunk: 16 units
           float hv[4], lv[4];
 #pragma unroll
           for (int e = 0; e < 4; e++) {
             const int u = c * TC_KC + g * 4 + e;
-            const float *wr = s_w0 + u * 5;
-            float acc = s_b0[u];
-#pragma unroll
-            for (int q = 0; q < 5; q++) if (q < dim) acc = fmaf(wr[q], xin[q], acc);
+            const float4 wa = *reinterpret_cast<const float4 *>(s_w0 + u * 8);      // bias, w0, w1, w2
+            const float4 wb = *reinterpret_cast<const float4 *>(s_w0 + u * 8 + 4);  // w3, w4, 0, 0
+            float acc = wa.x;
+            acc = fmaf(wa.y, xin[0], acc);
+            acc = fmaf(wa.z, xin[1], acc);
+            acc = fmaf(wa.w, xin[2], acc);
+            if (dim > 3) acc = fmaf(wb.x, xin[3], acc);
+            if (dim > 4) acc = fmaf(wb.y, xin[4], acc);
             acc = fmaxf(acc, 0.f);
             hv[e] = tf32_rna(acc);
             lv[e] = tf32_rna(acc - hv[e]);
           }
-          *reinterpret_cast<float4 *>(a_hi + g * 2048 + tid * 16) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-          *reinterpret_cast<float4 *>(a_lo + g * 2048 + tid * 16) = make_float4(lv[0], lv[1], lv[2], lv[3]);
+          *reinterpret_cast<float4 *>(a_hi + g * 2048 + row * 16) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+          *reinterpret_cast<float4 *>(a_lo + g * 2048 + row * 16) = make_float4(lv[0], lv[1], lv[2], lv[3]);
         }
         if (s) use1 = use + 1; else use0 = use + 1;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
@@ -271,13 +278,16 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float part = 0.f;
 #pragma unroll 1
-      for (int cb = 0; cb < TC_H; cb += 32) {
+      for (int cb = half * 64; cb < half * 64 + 64; cb += 32) {  // this thread's half of the 128 columns
         float v[32];
-        tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb, v);
+        tmem_ld32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)cb, v);
 #pragma unroll
         for (int k = 0; k < 32; k++) part = fmaf(s_w2[cb + k], fmaxf(v[k] + s_b1[cb + k], 0.f), part);
       }
-      if (p < npairs) s_logit[p] = part + W.b2;
+      if (half) s_part[row] = part;
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
+      if (!half && p < npairs) s_logit[p] = (part + s_part[row]) + W.b2;
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();  // every row has left tensor memory before the next tile overwrites it
     }
