@@ -33,6 +33,7 @@ struct KParams {
   int64_t env_id_offset;      // global id of env 0 (RNG key only)
   double x_max, y_max;
   double dtv_u, dtv_t;        // dt*v_max of UAVs / targets (Python evaluates dt*v_max first)
+  double dt, uav_h_max;       // for actions outside the precomputed table
   double dc, dp, two_dp;      // two_dp = radio*dp, radio = 2 (src/agent/uav.py:214)
   double tv, uv;              // target / uav v_max
   double s_dp_le, s_dp_lt, s_dc_le, s_2dp_le;  // exact squared thresholds

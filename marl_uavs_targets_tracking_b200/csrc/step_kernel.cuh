@@ -481,11 +481,17 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
       V.opos()[i] = make_double2(x, y); V.ohd()[i] = make_double2(ch, sh); V.oa()[i] = a_old;
       x += P.dtv_u * ch;
       y += P.dtv_u * sh;
-      h += S.dth[3 * act];
-      h = wrap_heading(h);
       // cos/sin of the new heading by angle addition (|error| ~ 3e-16; they only feed the observation).
       // The next step re-evaluates sincos from the stored heading, so the trajectory is unaffected.
-      const double cd = S.dth[3 * act + 1], sd = S.dth[3 * act + 2];
+      double dh, cd, sd;
+      if ((unsigned)act < (unsigned)P.na) {
+        dh = S.dth[3 * act]; cd = S.dth[3 * act + 1]; sd = S.dth[3 * act + 2];
+      } else {  // the reference's formula accepts any integer (uav.py:73-81); off-table actions take it literally
+        dh = P.dt * ((double)(2 * (act + 1) - P.na - 1) * P.uav_h_max / (double)(P.na - 1));
+        sincos_shared(dh, &sd, &cd);
+      }
+      h += dh;
+      h = wrap_heading(h);
       V.npos()[i] = make_double2(x, y);
       V.nhd()[i] = make_double2(ch * cd - sh * sd, sh * cd + ch * sd);
       V.na_()[i] = act;

@@ -95,6 +95,7 @@ extern "C" int uavsim_create(const UavSimParams *p, int64_t n_envs, int64_t env_
   k.E = n_envs; k.env_id_offset = env_id_offset;
   k.x_max = p->x_max; k.y_max = p->y_max;
   k.dtv_u = p->dt * p->uav_v_max;
+  k.dt = p->dt; k.uav_h_max = p->uav_h_max;
   k.dtv_t = p->dt * p->tgt_v_max;
   k.dc = p->dc; k.dp = p->dp; k.two_dp = 2 * p->dp;
   k.tv = p->tgt_v_max; k.uv = p->uav_v_max;

@@ -152,6 +152,62 @@ def test_origin_corner_in_the_warp_uniform_kernel(oracle):
     env.close()
 
 
+@pytest.mark.parametrize("n,m", [(64, 64), (10, 10), (20, 7)])
+def test_entities_beyond_the_prefilter_radius(oracle, n, m):
+    """The fp32 prefilter is only proven within 32 768 m of the map centre; environments with an entity outside
+    bypass it.  Mix near and very far entities and check masks-derived integers and values against the oracle."""
+    from marl_uavs_targets_tracking_b200 import default_config
+    cfg = default_config("MAAC-G", n, m)
+    E = 8
+    env = _env(n, m, cfg, E, track_counts=True, seed=4)
+    env.reset(cfg)
+    st = env.get_state()
+    st["ux"][1, 0] = 5.0e4                      # one UAV far away: whole environment 1 takes the bypass
+    st["ux"][2, :] += 1.0e5                     # a whole swarm far away (relative geometry intact)
+    st["tx"][2, :] += 1.0e5
+    st["tx"][3, 1], st["ty"][3, 1] = -4.0e4, 9.0e4   # a far target
+    st["ux"][5, :] += 3.0e4                     # inside the radius but large magnitude (prefilter still on)
+    st["tx"][5, :] += 3.0e4
+    env.set_state(cfg, *(st[k] for k in ("ux", "uy", "uh", "ua", "tx", "ty", "th")))
+    P = oracle_params_from_config(cfg, n, m)
+    host = {k: np.ascontiguousarray(v.cpu().numpy()) for k, v in env.get_state().items()}
+    for t in range(5):
+        a = env.random_actions(3, t).cpu().numpy().copy()
+        obs, rew4, cov = env.step_device(cfg, None)
+        ref = oracle.step_batch(P, 1, float(cfg["cooperative"]), None, host, a, nthreads=4)
+        assert np.array_equal(cov.cpu().numpy(), ref["covered"])
+        assert np.array_equal(env.tracker_counts.cpu().numpy(), ref["tracker_cnt"])
+        # positions ~1e5: the observation's self part x/dc is ~200, compare with the scaled rule
+        assert max_scaled_err(obs.double().cpu().numpy(), ref["obs"]) <= TOL_TIGHT
+        assert max_scaled_err(rew4.double().cpu().numpy(), ref["rew4"]) <= TOL_TIGHT
+    env.close()
+
+
+def test_unusual_actions_and_time_steps(oracle):
+    """dt * rate beyond a full turn (general fmod path of the heading wrap) and action indices outside
+    {0..na-1} (the reference's formula accepts any integer, uav.py:73-81)."""
+    from marl_uavs_targets_tracking_b200 import default_config
+    n, m = 12, 9
+    cfg = default_config("MAAC-G", n, m, uav__dt=37.0, uav__v_max=3.0)
+    env = _env(n, m, cfg, 5, track_counts=True, seed=6)
+    env.reset(cfg)
+    P = oracle_params_from_config(cfg, n, m)
+    host = {k: np.ascontiguousarray(v.cpu().numpy()) for k, v in env.get_state().items()}
+    rng = np.random.RandomState(0)
+    for t in range(6):
+        a = rng.randint(-5, 30, size=(5, n)).astype(np.int32)   # mostly outside 0..11
+        obs, rew4, cov = env.step_device(cfg, None, torch.as_tensor(a, device="cuda:0"))
+        ref = oracle.step_batch(P, 1, float(cfg["cooperative"]), None, host, a, nthreads=2)
+        got = env.get_state()
+        for k in ("ux", "uy", "uh"):
+            assert max_scaled_err(got[k].cpu().numpy(), host[k]) <= 1e-12, k
+        assert np.array_equal(got["ua"].cpu().numpy(), host["ua"])
+        assert np.array_equal(cov.cpu().numpy(), ref["covered"])
+        assert max_scaled_err(obs.double().cpu().numpy(), ref["obs"]) <= TOL_TIGHT
+        assert max_scaled_err(rew4.double().cpu().numpy(), ref["rew4"]) <= TOL_TIGHT
+    env.close()
+
+
 def test_long_episode_64x64_does_not_stall():
     """A full 200-step episode at 64x64 with many environments (UAVs do reach the origin corner)."""
     from marl_uavs_targets_tracking_b200 import default_config
