@@ -63,6 +63,7 @@ struct CtaSmem {
   float *obs;          // [epb*n*12]
   int *tcnt;           // [epb*m] UAVs strictly within dp of each target
   int *far;            // [epb] 1 if an entity is farther than KParams::rmax from the map centre
+  int *cov;            // [epb] covered targets
 };
 
 static size_t step_smem_bytes(int n, int m, int na, int epb) {
@@ -70,7 +71,7 @@ static size_t step_smem_bytes(int n, int m, int na, int epb) {
   size_t b = (size_t)epb * L.stride;
   b += ((size_t)epb * n + 3 * (size_t)na + 64) * 8 + 8;
   b += (size_t)epb * n * 12 * 4;
-  b += ((size_t)epb * m + (size_t)epb) * 4;
+  b += ((size_t)epb * m + 2 * (size_t)epb) * 4;
   return b + 16;
 }
 
@@ -85,7 +86,8 @@ __device__ __forceinline__ CtaSmem carve(unsigned char *base, int n, int m, int 
   s.obs = reinterpret_cast<float *>(d);
   int *ip = reinterpret_cast<int *>(s.obs + (size_t)epb * n * 12);
   s.tcnt = ip; ip += (size_t)epb * m;
-  s.far = ip;
+  s.far = ip; ip += epb;
+  s.cov = ip;
   return s;
 }
 
@@ -416,8 +418,11 @@ __device__ __forceinline__ void agent_fast(const KParams &P, const UavSimBuffers
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
+#ifndef UAVSIM_WARPS_PER_SM
+#define UAVSIM_WARPS_PER_SM 32   // 64 registers per thread: measured best of 16 / 20 / 24 / 32 resident warps per SM
+#endif
 template <int CN, int CM, bool MASKS, int NT>
-__global__ void __launch_bounds__(NT, 768 / NT)
+__global__ void __launch_bounds__(NT, UAVSIM_WARPS_PER_SM * 32 / NT)
 uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restrict__ g_dth, int64_t env_begin,
                    int64_t env_count, int epb, int mode, double coop, int done_flag,
                    double *__restrict__ stats_partial) {
@@ -439,7 +444,7 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
   for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
     const int64_t e0 = env_begin + grp * epb;
     const int ne = (int)min((int64_t)epb, env_begin + env_count - e0);
-    if (tid < epb) S.far[tid] = 0;  // (every phase-1 reader of the previous iteration has passed a barrier)
+    if (tid < epb) { S.far[tid] = 0; S.cov[tid] = 0; }  // (their readers of the previous iteration have passed a barrier)
     __syncthreads();                // previous iteration's readers are done; dth table visible
 
     // ---- phase 0a: targets (src/agent/target.py:27-60) ----
@@ -567,22 +572,25 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
       B.rew4[3 * plane + gi] = (float)dupn;
       st_tt += ttn; st_bp += bpn; st_dup += dupn;
     }
-    if (tid < ne) {  // environment.py:246-253: targets with at least one UAV strictly within dp
-      int c = 0;
-      const int *tc = S.tcnt + tid * m;
-      for (int t = 0; t < m; t++) c += (tc[t] > 0);
+    // environment.py:246-253: targets with at least one UAV strictly within dp, counted cooperatively
+    for (int k = tid; k < ne * m; k += NT) {
+      const int c = S.tcnt[k];
+      if (c > 0) atomicAdd(&S.cov[k / m], 1);
+      if (B.tracker_cnt) B.tracker_cnt[e0 * m + k] = c;
+    }
+    {  // coalesced observation write: ne*n*12 floats = ne*n*3 float4, contiguous in global memory
+      const float4 *src = reinterpret_cast<const float4 *>(S.obs);
+      float4 *dst = reinterpret_cast<float4 *>(B.obs + e0 * n * 12);
+      for (int k = tid; k < ne * n * 3; k += NT) dst[k] = src[k];
+    }
+    __syncthreads();
+    if (tid < ne) {
+      const int c = S.cov[tid];
       B.covered[e0 + tid] = c;
       if (B.done) B.done[e0 + tid] = done_flag;
       st_cov += (double)c;
       st_cmax = max(st_cmax, c);
       st_envs += 1.0;
-    }
-    if (B.tracker_cnt)
-      for (int k = tid; k < ne * m; k += NT) B.tracker_cnt[e0 * m + k] = S.tcnt[k];
-    {  // coalesced observation write: ne*n*12 floats = ne*n*3 float4, contiguous in global memory
-      const float4 *src = reinterpret_cast<const float4 *>(S.obs);
-      float4 *dst = reinterpret_cast<float4 *>(B.obs + e0 * n * 12);
-      for (int k = tid; k < ne * n * 3; k += NT) dst[k] = src[k];
     }
   }
   block_stats_commit(S.red, stats_partial + (size_t)blockIdx.x * STAT_W, st_r, st_tt, st_bp, st_dup, st_cov, st_cmax,
