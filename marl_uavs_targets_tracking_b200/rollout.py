@@ -1,0 +1,100 @@
+"""Batched rollout on the GPU-resident environment.
+
+The reference rolls one environment out with a per-agent, batch-of-one policy forward and an `.item()` sync per
+action (src/train.py:160-176, src/models/actor_critic.py:138-148).  Here every step is one `[E*n, 12]` actor
+forward, one on-device categorical sample and one `uavsim_step` launch; observations, actions and rewards never
+leave HBM.  The learner is stock PyTorch with the reference's architecture and one-step TD actor-critic update
+(src/models/actor_critic.py:85-179): it is the consumer of the accelerated path, not part of it.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .distributed import episode_summary, reduce_episode_stats
+
+
+class PolicyNet(nn.Module):
+    """12 -> H -> na softmax policy (FnnPolicyNet, src/models/actor_critic.py:85-99)."""
+
+    def __init__(self, n_states, n_hiddens, n_actions):
+        super().__init__()
+        self.fc1 = nn.Linear(n_states, n_hiddens)
+        self.fc2 = nn.Linear(n_hiddens, n_actions)
+
+    def forward(self, x):
+        return F.softmax(self.fc2(F.relu(self.fc1(x))), dim=1)
+
+
+class ValueNet(nn.Module):
+    """12 -> H -> 1 critic (FnnValueNet, src/models/actor_critic.py:102-113)."""
+
+    def __init__(self, n_states, n_hiddens):
+        super().__init__()
+        self.fc1 = nn.Linear(n_states, n_hiddens)
+        self.fc2 = nn.Linear(n_hiddens, 1)
+
+    def forward(self, x):
+        return self.fc2(F.relu(self.fc1(x))).squeeze(1)
+
+
+class BatchedActorCritic:
+    """Same constructor and update rule as the reference `ActorCritic` (src/models/actor_critic.py:116-179), but
+    `take_actions` works on all agents of all environments at once and `update` takes device tensors."""
+
+    def __init__(self, state_dim, hidden_dim, action_dim, actor_lr, critic_lr, gamma, device, ddp=False):
+        self.actor = PolicyNet(state_dim, hidden_dim, action_dim).to(device)
+        self.critic = ValueNet(state_dim, hidden_dim).to(device)
+        if ddp:  # gradient all-reduce over NCCL when several ranks train one policy
+            from torch.nn.parallel import DistributedDataParallel as DDP
+            self.actor = DDP(self.actor, device_ids=[torch.device(device).index])
+            self.critic = DDP(self.critic, device_ids=[torch.device(device).index])
+        self.actor_optimizer = torch.optim.Adam(self.actor.parameters(), lr=actor_lr)
+        self.critic_optimizer = torch.optim.Adam(self.critic.parameters(), lr=critic_lr)
+        self.gamma, self.device = gamma, device
+
+    @torch.no_grad()
+    def take_actions(self, states):
+        """states [B,12] float -> (actions [B] int32, probs [B,na])."""
+        probs = self.actor(states)
+        actions = torch.multinomial(probs, 1).squeeze(1)  # Categorical(probs).sample()
+        return actions.to(torch.int32), probs
+
+    def update(self, states, actions, rewards, next_states):
+        """One-step TD actor-critic update on [B,...] device tensors (src/models/actor_critic.py:150-179)."""
+        td_target = rewards + self.gamma * self.critic(next_states)
+        td_delta = td_target - self.critic(states)
+        log_probs = torch.log(self.actor(states).gather(1, actions.long().view(-1, 1)))
+        actor_loss = torch.mean(-log_probs * td_delta.detach())
+        critic_loss = F.mse_loss(self.critic(states), td_target.detach())
+        self.actor_optimizer.zero_grad()
+        self.critic_optimizer.zero_grad()
+        actor_loss.backward()
+        critic_loss.backward()
+        self.actor_optimizer.step()
+        self.critic_optimizer.step()
+        return actor_loss.detach(), critic_loss.detach(), td_delta.detach()
+
+
+def operate_epoch_batched(config, env, agent, pmi, num_steps, keep_transitions=True):
+    """One episode for all environments of `env` (the batched form of src/train.py:142-196).
+
+    Returns (transitions, summary): transitions = dict of device tensors states [T*E*n,12], actions [T*E*n],
+    rewards [T*E*n], next_states [T*E*n,12] (None if keep_transitions is False); summary = the six scalars the
+    reference logs per episode, averaged over every environment of every rank."""
+    E, n = env.n_envs, env.n_uav
+    states = env.get_states().reshape(E * n, 12).clone()
+    bufs = {"states": [], "actions": [], "rewards": [], "next_states": []} if keep_transitions else None
+    for step in range(num_steps):
+        config["step"] = step + 1
+        actions, _ = agent.take_actions(states)
+        obs, rew4, _ = env.step_device(config, pmi, actions.view(E, n))
+        next_states = obs.reshape(E * n, 12)
+        if keep_transitions:
+            bufs["states"].append(states)
+            bufs["actions"].append(actions)
+            bufs["rewards"].append(rew4[0].reshape(E * n).clone())
+            bufs["next_states"].append(next_states.clone())
+        states = next_states.clone()
+    stats = reduce_episode_stats(env.episode_stats(), device=env.device)
+    transitions = {k: torch.cat(v) for k, v in bufs.items()} if keep_transitions else None
+    return transitions, episode_summary(stats, n)
