@@ -64,7 +64,9 @@ class BatchedActorCritic:
         td_target = rewards + self.gamma * self.critic(next_states)
         td_delta = td_target - self.critic(states)
         log_probs = torch.log(self.actor(states).gather(1, actions.long().view(-1, 1)))
-        actor_loss = torch.mean(-log_probs * td_delta.detach())
+        # The reference multiplies log_probs [B,1] by td_delta [B]: that broadcasts to a [B,B] outer product whose mean
+        # is mean(-log_probs) * mean(td_delta) (src/models/actor_critic.py:171).  Same value and gradient, O(B) memory.
+        actor_loss = torch.mean(-log_probs) * torch.mean(td_delta.detach())
         critic_loss = F.mse_loss(self.critic(states), td_target.detach())
         self.actor_optimizer.zero_grad()
         self.critic_optimizer.zero_grad()
