@@ -208,8 +208,9 @@ def measure_workload(torch, dist, env_cls, args, name, rank, world, device, step
     pmi = make_pmi(torch) if method == "MAAC-R" else None
     env = env_cls(n, m, 2000, 2000, 12, n_envs=E, device=device, env_id_offset=rank * E, seed=42, num_steps=EPISODE)
     env.reset(cfg)
-    # random-policy actions resident in HBM: a bank of NB pre-drawn [E,n] tensors, rebound per step (no copy)
-    NB = 8
+    # random-policy actions resident in HBM: one pre-drawn [E,n] tensor per step of an episode (a short bank that
+    # repeats would make every UAV fly the same few turns in a loop instead of a random walk), rebound per step
+    NB = min(EPISODE, steps + warmup)
     bank = torch.empty((NB, E, n), dtype=torch.int32, device=device)
     for b in range(NB):
         env.bind_actions(bank[b])
@@ -260,17 +261,18 @@ def measure_workload(torch, dist, env_cls, args, name, rank, world, device, step
            "launches": launches, "clocks": clocks, "value": E * world * n * steps / (ms * 1e-3), "trace": trace}
 
     if with_e2e:
-        h_act = torch.empty((NB, E, n), dtype=torch.int32).pin_memory()
-        h_act.copy_(bank.cpu())
+        NH = min(NB, e2e_steps + 2)
+        h_act = torch.empty((NH, E, n), dtype=torch.int32).pin_memory()
+        h_act.copy_(bank[:NH].cpu())
         h_obs = torch.empty((E, n, 12), dtype=torch.float32).pin_memory()
         h_rew = torch.empty((4, E, n), dtype=torch.float32).pin_memory()
         h_cov = torch.empty((E,), dtype=torch.int32).pin_memory()
         for i in range(2):
-            env.step_host(cfg, pmi, h_act[i % NB], h_obs, h_rew, h_cov, chunks=args.chunks)
+            env.step_host(cfg, pmi, h_act[i % NH], h_obs, h_rew, h_cov, chunks=args.chunks)
         barrier()
         t0 = time.perf_counter()
         for i in range(e2e_steps):
-            env.step_host(cfg, pmi, h_act[i % NB], h_obs, h_rew, h_cov, chunks=args.chunks)
+            env.step_host(cfg, pmi, h_act[(i + 2) % NH], h_obs, h_rew, h_cov, chunks=args.chunks)
         torch.cuda.synchronize(device)
         dt = time.perf_counter() - t0
         if world > 1:
