@@ -47,8 +47,8 @@ __host__ __device__ constexpr EnvLayout env_layout(int n, int m) {
   L.nhd = o; o += 16 * n;    // double2 (cos h, sin h) after the move
   L.opos = o; o += 16 * n;   // before the move
   L.ohd = o; o += 16 * n;
-  L.tposf = o; o += 8 * m;   // float2 target position relative to the map centre
-  L.nposf = o; o += 8 * n;   // float2 new UAV position relative to the map centre
+  L.tposf = o; o += 16 * ((m + 1) / 2);  // fp32 target positions relative to the map centre, two per float4 {x0, x1, y0, y1}
+  L.nposf = o; o += 16 * ((n + 1) / 2);  // fp32 new UAV positions, same pairing (operands of the packed f32x2 prefilter)
   L.na_ = o; o += 4 * n;     // new action index
   L.oa = o; o += 4 * n;      // previous action index
   L.stride = (o + 15) & ~15;
@@ -101,8 +101,17 @@ struct EnvView {
   __device__ __forceinline__ double2 *nhd() const { return reinterpret_cast<double2 *>(b + L.nhd); }
   __device__ __forceinline__ double2 *opos() const { return reinterpret_cast<double2 *>(b + L.opos); }
   __device__ __forceinline__ double2 *ohd() const { return reinterpret_cast<double2 *>(b + L.ohd); }
-  __device__ __forceinline__ float2 *tposf() const { return reinterpret_cast<float2 *>(b + L.tposf); }
-  __device__ __forceinline__ float2 *nposf() const { return reinterpret_cast<float2 *>(b + L.nposf); }
+  __device__ __forceinline__ float4 *tposf() const { return reinterpret_cast<float4 *>(b + L.tposf); }
+  __device__ __forceinline__ float4 *nposf() const { return reinterpret_cast<float4 *>(b + L.nposf); }
+  // entity j of a paired array: pair j/2, slot j%2 (x at float slot, y two floats later)
+  __device__ __forceinline__ static void put_pair(float4 *arr, int j, float x, float y) {
+    float *f = reinterpret_cast<float *>(arr + (j >> 1)) + (j & 1);
+    f[0] = x; f[2] = y;
+  }
+  __device__ __forceinline__ static float2 get_pair(const float4 *arr, int j) {
+    const float *f = reinterpret_cast<const float *>(arr + (j >> 1)) + (j & 1);
+    return make_float2(f[0], f[2]);
+  }
   __device__ __forceinline__ int *na_() const { return reinterpret_cast<int *>(b + L.na_); }
   __device__ __forceinline__ int *oa() const { return reinterpret_cast<int *>(b + L.oa); }
 };
@@ -229,36 +238,43 @@ struct CommAcc {
 
 __device__ __forceinline__ uint32_t low_bits(int len) { return len >= 32 ? 0xffffffffu : ((1u << len) - 1u); }
 
-// (A) fp32 prefilter over one chunk of partner positions: three candidate masks for three guarded thresholds
-// t0 <= t1 <= t2.  Code size matters here (the kernel is instruction-fetch sensitive): 8 partners per loop
-// trip with compile-time bits, the byte shifted into place once per trip.
-__device__ __forceinline__ void prefilter(const float2 *__restrict__ pf, int len, float xf, float yf, float t0, float t1,
-                                          float t2, uint32_t &m0, uint32_t &m1, uint32_t &m2) {
-  m0 = m1 = m2 = 0;
+// (A) fp32 prefilter over one chunk of partner positions: candidate mask for a guarded squared threshold.
+// Blackwell's packed fp32 pipe does two partners per instruction (sub/mul/fma.f32x2 -> FADD2 / FMUL2 / FFMA2, each
+// half an ordinary IEEE fp32 operation, so the error bound behind the guard is unchanged); partners are stored two
+// per float4 {x0, x1, y0, y1}.  `pf` points at the pair holding partner 0 of the chunk (chunks start on even
+// indices); a trailing odd slot holds +huge and can never pass.  Code size matters (the kernel is
+// instruction-fetch sensitive): UAVSIM_PF_UNROLL partners per loop trip with compile-time bits.
+#ifndef UAVSIM_PF_UNROLL
+#define UAVSIM_PF_UNROLL 16
+#endif
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  return (uint64_t)__float_as_uint(lo) | ((uint64_t)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ uint32_t prefilter(const float4 *__restrict__ pf, int len, float xf, float yf, float thr) {
+  constexpr int U = UAVSIM_PF_UNROLL;
+  const uint64_t xf2 = pack2(xf, xf), yf2 = pack2(yf, yf);
+  uint32_t mask = 0;
+  auto pair_bits = [&](int k) -> uint32_t {  // partners 2k, 2k+1 of the chunk -> two bits
+    const float4 p = pf[k];
+    uint64_t dx, dy, d2;
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(pack2(p.x, p.y)), "l"(xf2));
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(pack2(p.z, p.w)), "l"(yf2));
+    asm("mul.f32x2 %0, %1, %1;" : "=l"(d2) : "l"(dy));
+    asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(d2) : "l"(dx), "l"(d2));
+    const float d2a = __uint_as_float((uint32_t)d2), d2b = __uint_as_float((uint32_t)(d2 >> 32));
+    return ((d2a <= thr) ? 1u : 0u) | ((d2b <= thr) ? 2u : 0u);
+  };
   int jj = 0;
 #pragma unroll 1
-  for (; jj + 8 <= len; jj += 8) {
-    uint32_t b0 = 0, b1 = 0, b2 = 0;
+  for (; jj + U <= len; jj += U) {
+    uint32_t b = 0;
 #pragma unroll
-    for (int u = 0; u < 8; u++) {
-      const float2 p = pf[jj + u];
-      const float dx = p.x - xf, dy = p.y - yf;
-      const float d2 = fmaf(dx, dx, dy * dy);
-      b0 |= (d2 <= t0) ? (1u << u) : 0u;
-      b1 |= (d2 <= t1) ? (1u << u) : 0u;
-      b2 |= (d2 <= t2) ? (1u << u) : 0u;
-    }
-    m0 |= b0 << jj; m1 |= b1 << jj; m2 |= b2 << jj;
+    for (int u = 0; u < U / 2; u++) b |= pair_bits(jj / 2 + u) << (2 * u);
+    mask |= b << jj;
   }
 #pragma unroll 1
-  for (; jj < len; jj++) {
-    const float2 p = pf[jj];
-    const float dx = p.x - xf, dy = p.y - yf;
-    const float d2 = fmaf(dx, dx, dy * dy);
-    m0 |= (d2 <= t0) ? (1u << jj) : 0u;
-    m1 |= (d2 <= t1) ? (1u << jj) : 0u;
-    m2 |= (d2 <= t2) ? (1u << jj) : 0u;
-  }
+  for (; jj < len; jj += 2) mask |= pair_bits(jj / 2) << jj;
+  return mask & low_bits(len);
 }
 
 // One chunk of up to 32 partner UAVs j = jb .. jb+len-1 for UAV i.  Partners with j < i moved before i: their
@@ -279,10 +295,9 @@ __device__ __forceinline__ uint32_t pair_chunk(const KParams &P, const UavSimBuf
   if (far_env) {
     cn = co = low_bits(len);
   } else {
-    uint32_t m_2dp, m_dc, m_dcmv;
-    prefilter(V.nposf() + jb, len, xf, yf, P.f_2dp, P.f_dc, P.f_dcmv, m_2dp, m_dc, m_dcmv);
-    cn = (m_dc & lt) | (m_2dp & ~lt);
-    co = m_dcmv;
+    // ONE guarded threshold, dc + dt*v, for both lists: finer masks (exactly dc for moved partners, 2dp for the
+    // reward-only evaluations) saved fewer exact evaluations than their extra compare + select cost on every pair
+    cn = co = prefilter(V.nposf() + jb / 2, len, xf, yf, P.f_dcmv);
   }
   cn &= ~self;
   co &= ~(lt | self);
@@ -338,7 +353,7 @@ __device__ __forceinline__ void agent_fast(const KParams &P, const UavSimBuffers
   const int n = CN ? CN : n_rt, m = CM ? CM : m_rt;
   const double2 me = V.npos()[i], mh = V.nhd()[i];
   const double xi = me.x, yi = me.y, chi = mh.x, shi = mh.y;
-  const float2 mef = V.nposf()[i];
+  const float2 mef = EnvView::get_pair(V.nposf(), i);
   const float xf = mef.x, yf = mef.y;
 
   // ---- targets: observe_target (uav.py:101-122), tracking reward (uav.py:199-212), coverage (environment.py:246-253)
@@ -350,9 +365,8 @@ __device__ __forceinline__ void agent_fast(const KParams &P, const UavSimBuffers
 #pragma unroll 1
     for (int tb = 0; tb < m; tb += 32) {
       const int len = min(32, m - tb);
-      uint32_t ct, u1, u2;
-      if (far_env) ct = low_bits(len);
-      else prefilter(V.tposf() + tb, len, xf, yf, P.f_dp, P.f_dp, P.f_dp, ct, u1, u2);
+      const uint32_t ct0 = far_env ? low_bits(len) : prefilter(V.tposf() + tb / 2, len, xf, yf, P.f_dp);
+      uint32_t ct = ct0;
       if (MASKS)
         for (int jj = 0; jj < len; jj++) { B.obs_mask[mrow_t + tb + jj] = 0; B.cover_mask[mrow_t + tb + jj] = 0; }
 #pragma unroll 1
@@ -435,6 +449,11 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
   const int64_t plane = P.E * n;  // rew4 plane stride
 
   for (int k = tid; k < 3 * P.na; k += NT) S.dth[k] = g_dth[k];
+  for (int k = tid; k < epb; k += NT) {  // odd trailing slots of the paired fp32 arrays: never a candidate
+    const EnvView V0{S.env + (size_t)k * L.stride, L};
+    if (m & 1) EnvView::put_pair(V0.tposf(), m, 3.0e18f, 3.0e18f);
+    if (n & 1) EnvView::put_pair(V0.nposf(), n, 3.0e18f, 3.0e18f);
+  }
 
   const int64_t ngroups = (env_count + epb - 1) / epb;
   // per-thread statistics, reduced once at the end (src/train.py:181-192)
@@ -468,7 +487,7 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
       V.tpos()[t] = make_double2(x, y);
       // cos(target.h) * target.v_max / self.v_max  (src/agent/uav.py:115-116)
       V.tvel()[t] = make_double2(ch * P.tv / P.uv, sh * P.tv / P.uv);
-      V.tposf()[t] = make_float2((float)(x - P.cx), (float)(y - P.cy));
+      EnvView::put_pair(V.tposf(), t, (float)(x - P.cx), (float)(y - P.cy));
       if (!(fabs(x - P.cx) <= P.rmax && fabs(y - P.cy) <= P.rmax)) S.far[te] = 1;
       S.tcnt[q] = 0;
     }
@@ -500,7 +519,7 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
       V.npos()[i] = make_double2(x, y);
       V.nhd()[i] = make_double2(ch * cd - sh * sd, sh * cd + ch * sd);
       V.na_()[i] = act;
-      V.nposf()[i] = make_float2((float)(x - P.cx), (float)(y - P.cy));
+      EnvView::put_pair(V.nposf(), i, (float)(x - P.cx), (float)(y - P.cy));
       // the prefilter's error bound assumes every entity within rmax of the map centre
       if (!(fabs(x - P.cx) <= P.rmax && fabs(y - P.cy) <= P.rmax)) S.far[el] = 1;
       B.ux[gi] = x; B.uy[gi] = y; B.uh[gi] = h; B.ua[gi] = act;

@@ -113,8 +113,6 @@ extern "C" int uavsim_create(const UavSimParams *p, int64_t n_envs, int64_t env_
   k.cx = p->x_max / 2; k.cy = p->y_max / 2;
   k.rmax = 32768.0;
   k.f_dp = prefilter_threshold(p->dp, k.rmax);
-  k.f_dc = prefilter_threshold(p->dc, k.rmax);
-  k.f_2dp = prefilter_threshold(2 * p->dp, k.rmax);
   k.f_dcmv = prefilter_threshold(p->dc + fabs(k.dtv_u) * (1.0 + 1e-9), k.rmax);
 
   // per action: dt * discrete_action(a) (src/agent/uav.py:73-81, :96) in the reference's evaluation order,
