@@ -75,19 +75,25 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Summarise the samples that arrived inside [t_begin, t_end] (the timed region); if the region was too short
+        for nvidia-smi to report inside it, fall back to every sample since start() (warm-up + timed region)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.25)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        window = "timed region"
+        rows = [ln for (ts, ln) in self.lines if t_begin is None or (t_begin <= ts <= (t_end or ts) + 0.15)]
+        if not rows:
+            rows, window = [ln for (_, ln) in self.lines], "warm-up + timed region"
         sm, mx, reasons, pw = [], [], set(), []
-        for ln in self.lines:
+        for ln in rows:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -100,7 +106,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def make_pmi(torch, hidden=128):
@@ -206,6 +212,8 @@ def measure_workload(torch, dist, env_cls, args, name, rank, world, device, step
         E = args.envs_per_gpu
     cfg = default_config(method, n, m)
     pmi = make_pmi(torch) if method == "MAAC-R" else None
+    sampler = ClockSampler(device.index)
+    sampler.start()  # early: nvidia-smi needs a moment to start streaming; only timed-region samples are reported
     env = env_cls(n, m, 2000, 2000, 12, n_envs=E, device=device, env_id_offset=rank * E, seed=42, num_steps=EPISODE)
     env.reset(cfg)
     # random-policy actions resident in HBM: one pre-drawn [E,n] tensor per step of an episode (a short bank that
@@ -234,8 +242,7 @@ def measure_workload(torch, dist, env_cls, args, name, rank, world, device, step
     barrier()
     l0 = env.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(device.index)
-    sampler.start()
+    t_begin = time.time()
     ev0.record(torch.cuda.current_stream(device))
     marks = []
     for i in range(steps):
@@ -246,7 +253,7 @@ def measure_workload(torch, dist, env_cls, args, name, rank, world, device, step
             marks.append(e)
     ev1.record(torch.cuda.current_stream(device))
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_begin, time.time())
     ms = ev0.elapsed_time(ev1)
     launches = env.launch_count() - l0
     trace = None
