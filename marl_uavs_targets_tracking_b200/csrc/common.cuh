@@ -80,7 +80,7 @@ struct uavsim {
   // tensor-core path (H = 128): fc1 pre-split into UMMA tiles
   bool has_tc;
   int pmi_path;        // 0 auto, 1 CUDA cores, 2 tensor cores
-  float *d_tc_tiles;   // fc1 tiles [24][2][128*16], then layer-0 tiles [2][384*16]
+  float *d_tc_tiles;   // [12][2][128*32]
   int tc_g;
   size_t smem_pmi;
   // host-buffer pipeline

@@ -328,9 +328,8 @@ static bool pmi_use_tensor(const uavsim_t *h) {
 
 static int pmi_tc_launch(uavsim_t *h, int64_t e0, int64_t cnt, double coop, cudaStream_t st) {
   PmiTcDev W;
-  W.b1 = h->pmi.b1; W.w2 = h->pmi.w2; W.b2 = h->pmi.b2;
+  W.w0 = h->pmi.w0; W.b0 = h->pmi.b0; W.b1 = h->pmi.b1; W.w2 = h->pmi.w2; W.b2 = h->pmi.b2;
   W.w1_tiles = h->d_tc_tiles;
-  W.w0_tiles = h->d_tc_tiles + (size_t)TC_NCHUNK * 2 * (TC_TILE_BYTES / 4);
   const int64_t ngroups = (cnt + h->tc_g - 1) / h->tc_g;
   int grid = (int)(ngroups < h->sm_count ? ngroups : h->sm_count);
   if (grid > h->stat_slots) grid = h->stat_slots;
@@ -398,13 +397,10 @@ extern "C" int uavsim_set_pmi_weights(uavsim_t *h, const UavSimPmiWeights *w, vo
   if (rc) return rc;
   h->has_tc = false;
   if (H == TC_H) {
-    // tensor-core path: weights split hi/lo (TF32) and laid out as the K-major UMMA tiles the kernel bulk-copies.
-    // fc1: chunk c of 16 inputs, part {hi, lo}, element (unit o, input k) at float (k/4)*512 + o*4 + (k%4).
-    // layer 0: one [384 x 16] tile per part, element (unit u, column k) at float (k/4)*1536 + u*4 + (k%4); columns
-    // 0..11 are the 12 inputs (block-diagonal: a branch only sees its own slice), column 12 the bias, 13..15 zero.
-    const size_t tile = TC_TILE_BYTES / 4, w0tile = TC_W0_BYTES / 4;
-    const size_t total_t = (size_t)TC_NCHUNK * 2 * tile + 2 * w0tile;
-    float *tiles = (float *)calloc(total_t, sizeof(float));
+    // tensor-core path: fc1 split hi/lo (TF32) and laid out as the K-major UMMA tiles the kernel bulk-copies:
+    // chunk c, part {hi, lo}, element (unit o, input k) at float (k/4)*512 + o*4 + (k%4)
+    const size_t tile = TC_TILE_BYTES / 4, total_t = (size_t)TC_NCHUNK * 2 * tile;
+    float *tiles = (float *)malloc(total_t * sizeof(float));
     for (int c = 0; c < TC_NCHUNK; c++)
       for (int o = 0; o < TC_H; o++)
         for (int kk = 0; kk < TC_KC; kk++) {
@@ -414,19 +410,6 @@ extern "C" int uavsim_set_pmi_weights(uavsim_t *h, const UavSimPmiWeights *w, vo
           tiles[((size_t)c * 2 + 0) * tile + e] = hi;
           tiles[((size_t)c * 2 + 1) * tile + e] = lo;
         }
-    float *w0t = tiles + (size_t)TC_NCHUNK * 2 * tile;
-    for (int uu = 0; uu < TC_H3; uu++) {
-      const int br = uu / TC_H, off = (br == 0) ? 0 : (br == 1 ? 5 : 9), dim = (br == 0) ? 5 : (br == 1 ? 4 : 3);
-      for (int kk = 0; kk < 16; kk++) {
-        float v = 0.f;
-        if (kk >= off && kk < off + dim) v = w->w0[(size_t)uu * 5 + (kk - off)];
-        else if (kk == 12) v = w->b0[uu];
-        const float hi = host_tf32_rna(v), lo = host_tf32_rna(v - hi);
-        const size_t e = (size_t)(kk / 4) * 1536 + (size_t)uu * 4 + (kk % 4);
-        w0t[e] = hi;
-        w0t[w0tile + e] = lo;
-      }
-    }
     if (!h->d_tc_tiles) CUDA_TRY(cudaMalloc(&h->d_tc_tiles, total_t * sizeof(float)));
     CUDA_TRY(cudaMemcpyAsync(h->d_tc_tiles, tiles, total_t * sizeof(float), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));
