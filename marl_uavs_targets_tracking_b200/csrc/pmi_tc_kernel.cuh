@@ -4,26 +4,34 @@
 // the folded PMINetwork (src/models/PMINet.py:41-62) maps la_i * la_j (12 values) to a logit; a float32 softmax
 // over each UAV's neighbours mixes their raw rewards (src/agent/uav.py:262-291).
 //
-// Mapping.  One CTA (256 threads) per SM, persistent over groups of environments.  Pair rows are processed in
-// tiles of 128 (threads r and r + 128 share row r = TMEM lane r: each computes half of every layer-0 chunk and
-// half of the epilogue columns).  The 384 -> 128 layer is a [128 x 384] x [384 x 128] GEMM per
-// tile, issued by one thread as tcgen05.mma.kind::tf32 (M = 128, N = 128, K = 8) with the fp32 accumulator in
-// tensor memory.  Precision: single-pass TF32 (10-bit mantissa) misses the 1e-5 bar, so
-// both operands are split x = hi + lo (hi = tf32(x), lo = tf32(x - hi)) and every K-slice runs three MMAs
-// hi*hi + lo*hi + hi*lo -- fp32-class products, fp32 accumulation.
-//   A (activations after layer 0): computed on CUDA cores per 32-unit K-chunk (block-diagonal 12 -> 384, <= 5 FMAs
-//     per unit), split, and written straight into the canonical K-major no-swizzle UMMA layout
+// Mapping.  One CTA per SM, persistent over groups of environments, warp-specialised:
+//   warp 0 (one elected lane)  fetches the fc1 weight chunks (cp.async.bulk, TMA engine) and issues every
+//                              tcgen05.mma (kind::tf32, M = 128, N = 128, K = 8); it never touches the data.
+//   warps 1..8 (256 threads)   two threads per pair row (row r = TMEM lane r): they build the row, run layer 0 on the
+//                              CUDA cores, write the A operand, and later do the epilogue.
+// The two sides meet only through mbarriers (A-ready / B-full / stage-free / accumulator-full / accumulator-free), so
+// the producers run ahead of the tensor pipe instead of stopping at a CTA-wide barrier per chunk, and with two
+// accumulators (2 x 128 TMEM columns) the epilogue of tile t overlaps the MMAs of tile t+1.
+// The 384 -> 128 layer is a [128 x 384] x [384 x 128] GEMM per tile of 128 pair rows, fp32 accumulator in tensor
+// memory.  Precision: single-pass TF32 (10-bit mantissa) misses the 1e-5 bar, so both operands
+// are split x = hi + lo (hi = tf32(x), lo = tf32(x - hi)) and every K-slice runs three MMAs hi*hi + lo*hi + hi*lo --
+// fp32-class products, fp32 accumulation.
+//   A (activations after layer 0): computed per 32-unit K-chunk (block-diagonal 12 -> 384, <= 5 FMAs per unit),
+//     split, and written straight into the canonical K-major no-swizzle UMMA layout
 //     byte(r, k) = (k/4)*2048 + (r/8)*128 + (r%8)*16 + (k%4)*4   (8x16-byte core matrices, LBO 2048, SBO 128)
-//     -- thread r writes one 16-byte vector per 4 units, consecutive threads consecutive vectors (no bank conflicts).
+//     -- a thread writes one 16-byte vector per 4 units, consecutive threads consecutive vectors (no bank conflicts).
 //   B (fc1 weights): pre-split and pre-arranged on the host in the same layout, one 32 KB block (hi | lo) per
-//     K-chunk, fetched with one cp.async.bulk (TMA engine, mbarrier complete_tx) per chunk.
-//   Two stages: the MMAs of chunk c run while the threads compute chunk c+1; tcgen05.commit releases a stage.
-// Epilogue: tcgen05.ld (32 lanes x 32 columns per warp and instruction) -> bias + ReLU -> dot with fc2 in the owning
-// thread (a thread holds a full row, no shuffles) -> logit in shared memory; then softmax + mix per UAV.
+//     K-chunk, mbarrier complete_tx.
+// Epilogue: tcgen05.ld (32 lanes x 32 columns per warp and instruction) -> bias + ReLU -> dot with fc2 in the two
+// owning threads -> logit in shared memory; then softmax + mix per UAV.
 #pragma once
 #include "common.cuh"
 
-#define TC_NT 256            // threads per CTA: 2 threads per pair row; warps w and w+4 share a TMEM lane quarter
+#ifndef TC_Q
+#define TC_Q 4               // producer threads per pair row; warps w, w+4, .. share a TMEM lane quarter
+#endif
+#define TC_NP (128 * TC_Q)   // producer / epilogue threads (warps 1 .. 4*TC_Q)
+#define TC_NT (TC_NP + 32)   // + warp 0 = control (TMA + MMA issue)
 #define TC_H 128
 #define TC_H3 384
 #define TC_KC 32             // hidden units per K-chunk
@@ -43,18 +51,21 @@ struct TcSmem {  // byte offsets inside dynamic shared memory (base is 1024-byte
   static constexpr uint32_t off = nbr + TC_AMAX * 16;                    // uint32 [AMAX+4]
   static constexpr uint32_t logit = off + (TC_AMAX + 4) * 4;             // float [PMAX]
   static constexpr uint32_t w0 = logit + TC_PMAX * 4;                    // float [384*8]: bias, 5 weights, 2 pad per unit
-  static constexpr uint32_t part = w0 + TC_H3 * 8 * 4;                   // float [128] partial fc2 dots of the upper half
-  static constexpr uint32_t b1 = part + 128 * 4;                         // float [128]
+  static constexpr uint32_t part = w0 + TC_H3 * 8 * 4;                   // float [3][128] partial fc2 dots of the other threads of a row
+  static constexpr uint32_t b1 = part + 3 * 128 * 4;                         // float [128]
   static constexpr uint32_t w2 = b1 + TC_H * 4;                          // float [128]
-  static constexpr uint32_t red = w2 + TC_H * 4;                         // double [64]
-  static constexpr uint32_t bar = red + 64 * 8;                          // 5 mbarriers + tmem pointer
-  static constexpr uint32_t total = bar + 64;
+  static constexpr uint32_t red = w2 + TC_H * 4;                         // double [7 per warp]
+  static constexpr uint32_t bar = red + (TC_NT / 32) * 7 * 8;                         // 10 mbarriers + tmem pointer
+  static constexpr uint32_t total = bar + 96;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -124,7 +135,10 @@ __global__ void __launch_bounds__(TC_NT, 1)
 uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, int64_t env_begin, int64_t env_count,
                      int G, double coop, double *__restrict__ stats_partial) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  const int n = P.n, tid = threadIdx.x, warp = tid >> 5, row = tid & 127, half = tid >> 7;
+  const int n = P.n, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool producer = warp > 0;
+  // producers: hardware warp w may only touch TMEM lanes 32*(w%4)..+31, so rows follow the warp id
+  const int row = 32 * (warp & 3) + lane, part_id = (warp - 1) >> 2, pt = tid - 32;
   float *s_obs = reinterpret_cast<float *>(smem + TcSmem::obs);
   double *s_raw = reinterpret_cast<double *>(smem + TcSmem::raw);
   uint64_t *s_nbr = reinterpret_cast<uint64_t *>(smem + TcSmem::nbr);
@@ -135,9 +149,11 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
   float *s_b1 = reinterpret_cast<float *>(smem + TcSmem::b1);
   float *s_w2 = reinterpret_cast<float *>(smem + TcSmem::w2);
   double *s_red = reinterpret_cast<double *>(smem + TcSmem::red);
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + TcSmem::bar + 48);
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + TcSmem::bar + 88);
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar_full0 = sbase + TcSmem::bar, bar_free0 = bar_full0 + 16, bar_acc = bar_full0 + 32;
+  const uint32_t bar0 = sbase + TcSmem::bar;
+  // [s] = stage, [a] = accumulator
+  const uint32_t bar_bfull = bar0, bar_aready = bar0 + 16, bar_free = bar0 + 32, bar_accfull = bar0 + 48, bar_accfree = bar0 + 64;
 
   for (int k = tid; k < TC_H3 * 8; k += TC_NT) {  // per unit: {bias, w0..w4, 0, 0} -> two 128-bit broadcast loads
     const int u = k >> 3, e = k & 7;
@@ -145,13 +161,17 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
   }
   for (int k = tid; k < TC_H; k += TC_NT) { s_b1[k] = W.b1[k]; s_w2[k] = W.w2[k]; }
   if (tid == 0) {
-    mbar_init(bar_full0, 1); mbar_init(bar_full0 + 8, 1);
-    mbar_init(bar_free0, 1); mbar_init(bar_free0 + 8, 1);
-    mbar_init(bar_acc, 1);
+    for (int k = 0; k < 2; k++) {
+      mbar_init(bar_bfull + 8 * k, 1);         // expect_tx by the control lane + TMA bytes
+      mbar_init(bar_aready + 8 * k, 4 * TC_Q);       // one arrive per producer warp
+      mbar_init(bar_free + 8 * k, 1);          // tcgen05.commit
+      mbar_init(bar_accfull + 8 * k, 1);       // tcgen05.commit
+      mbar_init(bar_accfree + 8 * k, 4 * TC_Q);      // one arrive per producer warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {  // tensor memory: 128 fp32 accumulator columns, allocated by one warp
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(128u) : "memory");
+  if (warp == 0) {  // tensor memory: two 128-column fp32 accumulators, allocated by one warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(256u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -159,8 +179,8 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *s_tmem;
 
-  uint32_t use0 = 0, use1 = 0;  // how often each stage has been filled (phase bookkeeping)
-  uint32_t tiles_done = 0;
+  uint32_t g = 0;   // K-chunks processed so far by this CTA (stage = g & 1, use = g >> 1): same sequence on both sides
+  uint32_t t = 0;   // tiles processed so far (accumulator = t & 1, use = t >> 1)
   const int64_t ngroups = (env_count + G - 1) / G;
   double st_r = 0;
 
@@ -177,155 +197,203 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
       s_off[a + 1] = __popcll(n0) + __popcll(n1);
     }
     __syncthreads();
-    if (warp == 0) {  // exclusive scan of the neighbour counts (A <= 512): 16 per lane + warp scan
-      const int per = (A + 31) / 32, lo = (tid & 31) * per;
+    if (warp == 1) {  // exclusive scan of the neighbour counts (A <= 512): 16 per lane + warp scan
+      const int per = (A + 31) / 32, lo = lane * per;
       uint32_t sum = 0;
       for (int k = 0; k < per; k++) if (lo + k < A) sum += s_off[lo + k + 1];
       uint32_t inc = sum;
-      for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if ((tid & 31) >= o) inc += v; }
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
       uint32_t run = inc - sum;
-      if (tid == 0) s_off[0] = 0;
+      if (lane == 0) s_off[0] = 0;
       for (int k = 0; k < per; k++) if (lo + k < A) { run += s_off[lo + k + 1]; s_off[lo + k + 1] = run; }
     }
     __syncthreads();
     const int npairs = (int)s_off[A];
+    const int ntiles = (npairs + 127) / 128;
 
-    for (int p0 = 0; p0 < npairs; p0 += 128) {
-      // ---- this thread's pair row: flat index -> (UAV a, its k-th neighbour b), x = la_a * la_b (uav.py:280-281)
-      float x[12];
-      const int p = p0 + row;
-      if (p < npairs) {
-        int lo = 0, hi = A;  // largest a with off[a] <= p
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= (uint32_t)p) lo = mid; else hi = mid; }
-        const int a = lo;
-        int k = p - (int)s_off[a];
-        uint64_t w = s_nbr[2 * a];
-        int base = (a / n) * n;
-        const int c0 = __popcll(w);
-        if (k >= c0) { k -= c0; w = s_nbr[2 * a + 1]; base += 64; }
-        for (int t = 0; t < k; t++) w &= w - 1;
-        const int b = base + __ffsll((long long)w) - 1;
+    if (!producer) {
+      // =============================== control warp: TMA + MMA issue ===============================
+      if (lane == 0) {
+        // fc1 chunk c into the stage of chunk number gg (the MMAs that last read that stage must be done)
+        auto load_b = [&](const uint32_t gg, const int c) {
+          const uint32_t s = gg & 1, use = gg >> 1;
+          if (use > 0) mbar_wait(bar_free + 8 * s, (use - 1) & 1);
+          mbar_expect_tx(bar_bfull + 8 * s, 2 * TC_TILE_BYTES);
+          bulk_g2s(sbase + TcSmem::stage + s * 4u * TC_TILE_BYTES + 2 * TC_TILE_BYTES,
+                   W.w1_tiles + (size_t)c * (2 * TC_TILE_BYTES / 4), 2 * TC_TILE_BYTES, bar_bfull + 8 * s);
+        };
+        if (ntiles > 0) load_b(g, 0);
+        for (int tile = 0; tile < ntiles; tile++, t++) {
+          const uint32_t acc = t & 1, d_tmem = tmem_d + 128u * acc;
+          for (int c = 0; c < TC_NCHUNK; c++, g++) {
+            const uint32_t s = g & 1, use = g >> 1;
+            const uint32_t stage = sbase + TcSmem::stage + s * 4u * TC_TILE_BYTES;
+            if (c == 0 && (t >> 1) > 0) mbar_wait(bar_accfree + 8 * acc, ((t >> 1) - 1) & 1);  // epilogue of tile t-2 done
+            mbar_wait(bar_aready + 8 * s, use & 1);  // producers have written A
+            mbar_wait(bar_bfull + 8 * s, use & 1);   // weights have landed
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t ah = stage, al = stage + TC_TILE_BYTES, bh = stage + 2 * TC_TILE_BYTES, bl = stage + 3 * TC_TILE_BYTES;
 #pragma unroll
-        for (int q = 0; q < 12; q++) x[q] = s_obs[a * 12 + q] * s_obs[b * 12 + q];
-      } else {
-#pragma unroll
-        for (int q = 0; q < 12; q++) x[q] = 0.f;
-      }
-
-      // ---- layer 1 GEMM, 12 K-chunks of 32 hidden units through the two stages.  The three input branches
-      //      (communication 5, observation 4, boundary/state 3 inputs; PMINet.py:45-58, BN folded) are unrolled
-      //      so the row stays in registers; each branch covers 4 chunks.
-      auto run_chunk = [&](const int c, const float *xin, const int dim) {
-        const int s = c & 1;
-        const uint32_t stage = sbase + TcSmem::stage + (uint32_t)s * 4u * TC_TILE_BYTES;
-        const uint32_t use = s ? use1 : use0;
-        if (use > 0) mbar_wait(bar_free0 + 8 * s, (use - 1) & 1);  // MMAs that read this stage have completed
-        if (tid == 0) {
-          mbar_expect_tx(bar_full0 + 8 * s, 2 * TC_TILE_BYTES);
-          bulk_g2s(stage + 2 * TC_TILE_BYTES, W.w1_tiles + (size_t)c * (2 * TC_TILE_BYTES / 4), 2 * TC_TILE_BYTES, bar_full0 + 8 * s);
-        }
-        unsigned char *a_hi = smem + TcSmem::stage + (size_t)s * 4 * TC_TILE_BYTES, *a_lo = a_hi + TC_TILE_BYTES;
-#pragma unroll 2
-        for (int g = half * 4; g < half * 4 + 4; g++) {  // this thread's half of the chunk: 16 units
-          float hv[4], lv[4];
-#pragma unroll
-          for (int e = 0; e < 4; e++) {
-            const int u = c * TC_KC + g * 4 + e;
-            const float4 wa = *reinterpret_cast<const float4 *>(s_w0 + u * 8);      // bias, w0, w1, w2
-            const float4 wb = *reinterpret_cast<const float4 *>(s_w0 + u * 8 + 4);  // w3, w4, 0, 0
-            float acc = wa.x;
-            acc = fmaf(wa.y, xin[0], acc);
-            acc = fmaf(wa.z, xin[1], acc);
-            acc = fmaf(wa.w, xin[2], acc);
-            if (dim > 3) acc = fmaf(wb.x, xin[3], acc);
-            if (dim > 4) acc = fmaf(wb.y, xin[4], acc);
-            acc = fmaxf(acc, 0.f);
-            hv[e] = tf32_rna(acc);
-            lv[e] = tf32_rna(acc - hv[e]);
+            for (int ks = 0; ks < TC_KC / 8; ks++) {  // one MMA consumes K = 8 = two 16-byte core-matrix columns
+              const uint32_t o = (uint32_t)ks * 2u * 2048u;
+              umma_tf32(d_tmem, umma_desc(ah + o), umma_desc(bh + o), (c | ks) ? 1u : 0u);
+#ifndef TC_ABL_MMA1
+              umma_tf32(d_tmem, umma_desc(al + o), umma_desc(bh + o), 1u);
+              umma_tf32(d_tmem, umma_desc(ah + o), umma_desc(bl + o), 1u);
+#endif
+            }
+            umma_commit(bar_free + 8 * s);                              // stage reusable when these MMAs are done
+            if (c == TC_NCHUNK - 1) umma_commit(bar_accfull + 8 * acc);  // accumulator complete
+            // weights of the next chunk stream in behind the MMAs just queued
+            if (c + 1 < TC_NCHUNK) load_b(g + 1, c + 1);
+            else if (tile + 1 < ntiles) load_b(g + 1, 0);
           }
-          *reinterpret_cast<float4 *>(a_hi + g * 2048 + row * 16) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-          *reinterpret_cast<float4 *>(a_lo + g * 2048 + row * 16) = make_float4(lv[0], lv[1], lv[2], lv[3]);
         }
-        if (s) use1 = use + 1; else use0 = use + 1;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+      }
+      __syncwarp();
+    } else {
+      // =============================== producers: rows, layer 0, epilogue ===============================
+      // epilogue of tile number `tt` (rows p0e..): bias + ReLU + fc2 (PMINet.py:59-62); the two threads of a row take
+      // 64 accumulator columns each.  It runs one tile late, after the first two chunks of the next tile have been
+      // produced, so the tensor pipe always has work queued while the accumulator is drained.
+      auto epilogue = [&](const uint32_t tt, const int p0e) {
+        const uint32_t acc_i = tt & 1;
+        mbar_wait(bar_accfull + 8 * acc_i, (tt >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float part = 0.f;
+#pragma unroll 1
+        for (int cb = part_id * (128 / TC_Q); cb < (part_id + 1) * (128 / TC_Q); cb += 32) {
+          float v[32];
+          tmem_ld32(tmem_d + 128u * acc_i + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)cb, v);
+#pragma unroll
+          for (int k = 0; k < 32; k++) part = fmaf(s_w2[cb + k], fmaxf(v[k] + s_b1[cb + k], 0.f), part);
+        }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
-          mbar_wait(bar_full0 + 8 * s, use & 1);  // fc1 chunk has landed
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t ah = stage, al = stage + TC_TILE_BYTES, bh = stage + 2 * TC_TILE_BYTES, bl = stage + 3 * TC_TILE_BYTES;
-#pragma unroll
-          for (int ks = 0; ks < TC_KC / 8; ks++) {  // one MMA consumes K = 8 = two 16-byte core-matrix columns
-            const uint32_t o = (uint32_t)ks * 2u * 2048u;
-            umma_tf32(tmem_d, umma_desc(ah + o), umma_desc(bh + o), (c | ks) ? 1u : 0u);
-            umma_tf32(tmem_d, umma_desc(al + o), umma_desc(bh + o), 1u);
-            umma_tf32(tmem_d, umma_desc(ah + o), umma_desc(bl + o), 1u);
-          }
-          umma_commit(bar_free0 + 8 * s);                  // stage reusable when these MMAs are done
-          if (c == TC_NCHUNK - 1) umma_commit(bar_acc);    // accumulator complete
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_accfree + 8 * acc_i);  // this warp's rows have left tensor memory
+        // combine the two halves of each row (producer-only named barrier: warp 0 is busy issuing MMAs)
+        if (part_id) s_part[(part_id - 1) * 128 + row] = part;
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_NP) : "memory");
+        if (!part_id && p0e + row < npairs) {
+          if (TC_Q == 4) s_logit[p0e + row] = ((part + s_part[row]) + (s_part[128 + row] + s_part[256 + row])) + W.b2;
+          else s_logit[p0e + row] = (part + s_part[row]) + W.b2;
         }
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_NP) : "memory");
       };
-#pragma unroll 1
-      for (int cc = 0; cc < 4; cc++) run_chunk(cc, x, 5);
-#pragma unroll 1
-      for (int cc = 4; cc < 8; cc++) run_chunk(cc, x + 5, 4);
-#pragma unroll 1
-      for (int cc = 8; cc < 12; cc++) run_chunk(cc, x + 9, 3);
 
-      // ---- epilogue: bias + ReLU + fc2 (PMINet.py:59-62), one accumulator row per thread
-      mbar_wait(bar_acc, tiles_done & 1);
-      tiles_done++;
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float part = 0.f;
-#pragma unroll 1
-      for (int cb = half * 64; cb < half * 64 + 64; cb += 32) {  // this thread's half of the 128 columns
-        float v[32];
-        tmem_ld32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)cb, v);
+      for (int tile = 0; tile < ntiles; tile++, t++) {
+        const int p0 = tile * 128;
+        // ---- this thread's pair row: flat index -> (UAV a, its k-th neighbour b), x = la_a * la_b (uav.py:280-281)
+        float x[12];
+        const int p = p0 + row;
+        if (p < npairs) {
+          int lo = 0, hi = A;  // largest a with off[a] <= p
+          while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= (uint32_t)p) lo = mid; else hi = mid; }
+          const int a = lo;
+          int k = p - (int)s_off[a];
+          uint64_t w = s_nbr[2 * a];
+          int base = (a / n) * n;
+          const int c0 = __popcll(w);
+          if (k >= c0) { k -= c0; w = s_nbr[2 * a + 1]; base += 64; }
+          for (int q = 0; q < k; q++) w &= w - 1;
+          const int b = base + __ffsll((long long)w) - 1;
 #pragma unroll
-        for (int k = 0; k < 32; k++) part = fmaf(s_w2[cb + k], fmaxf(v[k] + s_b1[cb + k], 0.f), part);
+          for (int q = 0; q < 12; q++) x[q] = s_obs[a * 12 + q] * s_obs[b * 12 + q];
+        } else {
+#pragma unroll
+          for (int q = 0; q < 12; q++) x[q] = 0.f;
+        }
+
+        // ---- layer 0 per K-chunk of 32 hidden units into the stage ring.  The three input branches
+        //      (communication 5, observation 4, boundary/state 3 inputs; PMINet.py:45-58, BN folded) are unrolled
+        //      so the row stays in registers; each branch covers 4 chunks.
+        auto run_chunk = [&](const int c, const float *xin, const int dim) {
+          const uint32_t s = g & 1, use = g >> 1;
+          if (use > 0) {  // MMAs that read this stage have completed
+            mbar_wait(bar_free + 8 * s, (use - 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
+          unsigned char *a_hi = smem + TcSmem::stage + (size_t)s * 4 * TC_TILE_BYTES, *a_lo = a_hi + TC_TILE_BYTES;
+#ifdef TC_ABL_NOPROD
+          if (c < 0)
+#endif
+#pragma unroll 2
+          for (int gq = part_id * (8 / TC_Q); gq < (part_id + 1) * (8 / TC_Q); gq++) {  // this thread's share of the chunk
+            float hv[4], lv[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              const int u = c * TC_KC + gq * 4 + e;
+              const float4 wa = *reinterpret_cast<const float4 *>(s_w0 + u * 8);      // bias, w0, w1, w2
+              const float4 wb = *reinterpret_cast<const float4 *>(s_w0 + u * 8 + 4);  // w3, w4, 0, 0
+              float acc = wa.x;
+              acc = fmaf(wa.y, xin[0], acc);
+              acc = fmaf(wa.z, xin[1], acc);
+              acc = fmaf(wa.w, xin[2], acc);
+              if (dim > 3) acc = fmaf(wb.x, xin[3], acc);
+              if (dim > 4) acc = fmaf(wb.y, xin[4], acc);
+              acc = fmaxf(acc, 0.f);
+              hv[e] = tf32_rna(acc);
+              lv[e] = tf32_rna(acc - hv[e]);
+            }
+            *reinterpret_cast<float4 *>(a_hi + gq * 2048 + row * 16) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+            *reinterpret_cast<float4 *>(a_lo + gq * 2048 + row * 16) = make_float4(lv[0], lv[1], lv[2], lv[3]);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_aready + 8 * s);
+          g++;
+        };
+#pragma unroll 1
+        for (int cc = 0; cc < 2; cc++) run_chunk(cc, x, 5);
+        if (tile > 0) epilogue(t - 1, p0 - 128);
+#pragma unroll 1
+        for (int cc = 2; cc < 4; cc++) run_chunk(cc, x, 5);
+#pragma unroll 1
+        for (int cc = 4; cc < 8; cc++) run_chunk(cc, x + 5, 4);
+#pragma unroll 1
+        for (int cc = 8; cc < 12; cc++) run_chunk(cc, x + 9, 3);
       }
-      if (half) s_part[row] = part;
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();
-      if (!half && p < npairs) s_logit[p] = (part + s_part[row]) + W.b2;
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();  // every row has left tensor memory before the next tile overwrites it
+      if (ntiles > 0) epilogue(t - 1, (ntiles - 1) * 128);
     }
     __syncthreads();
+    // the control lane advanced g and t privately; publish them to its warp (the producers counted on their own)
+    if (!producer) { g = __shfl_sync(0xffffffffu, g, 0); t = __shfl_sync(0xffffffffu, t, 0); }
 
     // ---- softmax over each UAV's neighbours (scipy.special.softmax on float32) and the mix (uav.py:284-290)
-    for (int a = tid; a < A; a += TC_NT) {
-      const uint32_t lo = s_off[a], hi = s_off[a + 1];
-      const double raw = s_raw[a];
-      double r;
-      if (hi > lo) {
-        float mx = s_logit[lo];
-        for (uint32_t q = lo + 1; q < hi; q++) mx = fmaxf(mx, s_logit[q]);
-        float ssum = 0.f;
-        for (uint32_t q = lo; q < hi; q++) ssum += expf(s_logit[q] - mx);
-        double acc = 0;
-        uint32_t q = lo;
-        const int base = (a / n) * n;
-        for (int half = 0; half < 2; half++) {
-          uint64_t w = s_nbr[2 * a + half];
-          while (w) {
-            const int j = __ffsll((long long)w) - 1;
-            w &= w - 1;
-            const float wgt = expf(s_logit[q] - mx) / ssum;
-            acc += s_raw[base + 64 * half + j] * (double)wgt;
-            q++;
+    if (producer) {
+      for (int a = pt; a < A; a += TC_NP) {
+        const uint32_t lo = s_off[a], hi = s_off[a + 1];
+        const double raw = s_raw[a];
+        double r;
+        if (hi > lo) {
+          float mx = s_logit[lo];
+          for (uint32_t q = lo + 1; q < hi; q++) mx = fmaxf(mx, s_logit[q]);
+          float ssum = 0.f;
+          for (uint32_t q = lo; q < hi; q++) ssum += expf(s_logit[q] - mx);
+          double acc = 0;
+          uint32_t q = lo;
+          const int base = (a / n) * n;
+          for (int hh = 0; hh < 2; hh++) {
+            uint64_t w = s_nbr[2 * a + hh];
+            while (w) {
+              const int j = __ffsll((long long)w) - 1;
+              w &= w - 1;
+              const float wgt = expf(s_logit[q] - mx) / ssum;
+              acc += s_raw[base + 64 * hh + j] * (double)wgt;
+              q++;
+            }
           }
+          r = (1 - coop) * raw + coop * acc;
+        } else {
+          r = (1 - coop) * raw;
         }
-        r = (1 - coop) * raw + coop * acc;
-      } else {
-        r = (1 - coop) * raw;
+        r = fmin(fmax(r, -1.0), 1.0);
+        B.rew4[e0 * n + a] = (float)r;
+        st_r += r;
       }
-      r = fmin(fmax(r, -1.0), 1.0);
-      B.rew4[e0 * n + a] = (float)r;
-      st_r += r;
     }
   }
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(128u) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(256u) : "memory");
   block_stats_commit(s_red, stats_partial + (size_t)blockIdx.x * STAT_W, st_r, 0, 0, 0, 0, 0, 0, TC_NT);
 }
