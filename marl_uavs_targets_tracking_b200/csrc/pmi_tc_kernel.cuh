@@ -5,59 +5,62 @@
 // over each UAV's neighbours mixes their raw rewards (src/agent/uav.py:262-291).
 //
 // Mapping.  One CTA per SM, persistent over groups of environments, warp-specialised:
-//   warp 0 (one elected lane)  fetches the fc1 weight chunks (cp.async.bulk, TMA engine) and issues every
-//                              tcgen05.mma (kind::tf32, M = 128, N = 128, K = 8); it never touches the data.
-//   warps 1..8 (256 threads)   two threads per pair row (row r = TMEM lane r): they build the row, run layer 0 on the
-//                              CUDA cores, write the A operand, and later do the epilogue.
-// The two sides meet only through mbarriers (A-ready / B-full / stage-free / accumulator-full / accumulator-free), so
-// the producers run ahead of the tensor pipe instead of stopping at a CTA-wide barrier per chunk, and with two
-// accumulators (2 x 128 TMEM columns) the epilogue of tile t overlaps the MMAs of tile t+1.
-// The 384 -> 128 layer is a [128 x 384] x [384 x 128] GEMM per tile of 128 pair rows, fp32 accumulator in tensor
-// memory.  Precision: single-pass TF32 (10-bit mantissa) misses the 1e-5 bar, so both operands
-// are split x = hi + lo (hi = tf32(x), lo = tf32(x - hi)) and every K-slice runs three MMAs hi*hi + lo*hi + hi*lo --
-// fp32-class products, fp32 accumulation.
-//   A (activations after layer 0): computed per 32-unit K-chunk (block-diagonal 12 -> 384, <= 5 FMAs per unit),
+//   warp 0 (one elected lane)  issues every tcgen05.mma (kind::tf32, M = 128, N = 128, K = 8) and the commits.
+//   warp 17 (one elected lane) streams the fc1 weight chunks into the ring (cp.async.bulk, TMA engine).
+//   warps 1..16 (512 threads)  one thread per pair row of a SET of four 128-row tiles (warp w: tile (w-1)/4, TMEM lane
+//                              quarter w%4): they build the row, run layer 0 on the CUDA cores, write the A operand,
+//                              and later do the epilogue.
+// The two sides meet only through mbarriers (A-ready / B-full / stage-free / accumulators-full / accumulators-free);
+// there is no CTA-wide barrier inside a set.
+// The 384 -> 128 layer is a [128 x 384] x [384 x 128] GEMM per tile, fp32 accumulators in tensor memory.  The four
+// tiles of a set own the four 128-column quarters of the SM's 512 TMEM columns and share every fc1 chunk: the fc1
+// matrix (393 KB split) does not fit in shared memory and streaming it from L2 once per TILE was the measured floor of
+// the previous version (44 GB/s per SM, 6.5 TB/s over the chip); once per SET is a quarter of that.
+// Precision: single-pass TF32 (10-bit mantissa) misses the 1e-5 bar, so both operands are split
+// x = hi + lo (hi = tf32(x), lo = tf32(x - hi)) and every K-slice runs three MMAs hi*hi + lo*hi + hi*lo -- fp32-class
+// products, fp32 accumulation.
+//   A (activations after layer 0): computed per 8-unit K-chunk into a 4-stage ring (block-diagonal 12 -> 384, <= 5 FMAs per unit),
 //     split, and written straight into the canonical K-major no-swizzle UMMA layout
 //     byte(r, k) = (k/4)*2048 + (r/8)*128 + (r%8)*16 + (k%4)*4   (8x16-byte core matrices, LBO 2048, SBO 128)
 //     -- a thread writes one 16-byte vector per 4 units, consecutive threads consecutive vectors (no bank conflicts).
-//   B (fc1 weights): pre-split and pre-arranged on the host in the same layout, one 32 KB block (hi | lo) per
-//     K-chunk, mbarrier complete_tx.
-// Epilogue: tcgen05.ld (32 lanes x 32 columns per warp and instruction) -> bias + ReLU -> dot with fc2 in the two
-// owning threads -> logit in shared memory; then softmax + mix per UAV.
+//   B (fc1 weights): pre-split and pre-arranged on the host in the same layout, one 8 KB block (hi | lo) per
+//     8-unit chunk = one bulk copy, mbarrier complete_tx.
+// Epilogue: tcgen05.ld (32 lanes x 32 columns per warp and instruction) -> bias + ReLU -> dot with fc2 in the row's
+// thread -> logit in shared memory; then softmax + mix per UAV.
 #pragma once
 #include "common.cuh"
 
-#ifndef TC_Q
-#define TC_Q 4               // producer threads per pair row; warps w, w+4, .. share a TMEM lane quarter
-#endif
-#define TC_NP (128 * TC_Q)   // producer / epilogue threads (warps 1 .. 4*TC_Q)
-#define TC_NT (TC_NP + 32)   // + warp 0 = control (TMA + MMA issue)
+#define TC_SET 4             // tiles per set = accumulators in tensor memory (4 x 128 columns)
+#define TC_NP (128 * TC_SET) // producer / epilogue threads (warps 1 .. 16)
+#define TC_NT (TC_NP + 64)   // + warp 0 = MMA issue, warp 17 = fc1 chunk loader (TMA)
 #define TC_H 128
 #define TC_H3 384
-#define TC_KC 32             // hidden units per K-chunk
+#define TC_KC 8              // hidden units per K-chunk = one MMA K-slice
+#define TC_NS 4              // stages of the operand ring
 #define TC_NCHUNK (TC_H3 / TC_KC)
-#define TC_TILE_BYTES 16384  // one 128 x 32 fp32 operand tile
-#define TC_AMAX 512          // UAVs per environment group
+#define TC_A_BYTES 4096      // one 128 x 8 fp32 operand block (hi or lo)
+#define TC_STAGE_BYTES ((2 * TC_SET + 2) * TC_A_BYTES)  // 4 x (A_hi, A_lo) + B_hi + B_lo = 40 KB
+#define TC_AMAX 256          // UAVs per environment group
 #define TC_PMAX 8192         // neighbour pairs per environment group
 
 // instruction descriptor: D = F32, A = B = TF32, K-major both, N = 128 (>>3 at bit 17), M = 128 (>>4 at bit 24)
 #define TC_IDESC ((1u << 4) | (2u << 7) | (2u << 10) | ((TC_H >> 3) << 17) | ((128u >> 4) << 24))
 
 struct TcSmem {  // byte offsets inside dynamic shared memory (base is 1024-byte aligned)
-  static constexpr uint32_t stage = 0;                                   // 2 x (A_hi, A_lo, B_hi, B_lo)
-  static constexpr uint32_t obs = 2 * 4 * TC_TILE_BYTES;                 // float [AMAX*12]
+  static constexpr uint32_t stage = 0;                                   // TC_NS x TC_STAGE_BYTES
+  static constexpr uint32_t obs = TC_NS * TC_STAGE_BYTES;                   // float [AMAX*12]
   static constexpr uint32_t raw = obs + TC_AMAX * 12 * 4;                // double [AMAX]
   static constexpr uint32_t nbr = raw + TC_AMAX * 8;                     // uint64 [AMAX*2]
   static constexpr uint32_t off = nbr + TC_AMAX * 16;                    // uint32 [AMAX+4]
   static constexpr uint32_t logit = off + (TC_AMAX + 4) * 4;             // float [PMAX]
   static constexpr uint32_t w0 = logit + TC_PMAX * 4;                    // float [384*8]: bias, 5 weights, 2 pad per unit
-  static constexpr uint32_t part = w0 + TC_H3 * 8 * 4;                   // float [3][128] partial fc2 dots of the other threads of a row
-  static constexpr uint32_t b1 = part + 3 * 128 * 4;                         // float [128]
+  static constexpr uint32_t b1 = w0 + TC_H3 * 8 * 4;                     // float [128]
   static constexpr uint32_t w2 = b1 + TC_H * 4;                          // float [128]
   static constexpr uint32_t red = w2 + TC_H * 4;                         // double [7 per warp]
-  static constexpr uint32_t bar = red + (TC_NT / 32) * 7 * 8;                         // 10 mbarriers + tmem pointer
-  static constexpr uint32_t total = bar + 96;
+  static constexpr uint32_t bar = red + (TC_NT / 32) * 7 * 8;            // 3 x TC_NS + 2 mbarriers + tmem pointer
+  static constexpr uint32_t total = bar + 128;
 };
+static_assert(TcSmem::total <= 232448, "tensor PMI kernel: shared memory over the 227 KB per-CTA limit");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -106,6 +109,34 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// The control warp runs its loop with all 32 lanes converged (warp-uniform control flow and operands, so the
+// descriptors live in uniform registers) and predicates the single-thread instructions on an elected lane INSIDE the
+// asm: a divergent `if (lane == 0)` around them makes the compiler wrap every tcgen05.mma in an ELECT / R2UR waterfall
+// loop, ~16 issue slots per MMA, which made the one issuing thread the bottleneck of the kernel.
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void umma_tf32_p(uint32_t lead, uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(TC_IDESC), "r"(accumulate), "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_p(uint32_t lead, uint32_t bar) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+               "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(lead) : "memory");
+}
+__device__ __forceinline__ void load_chunk_p(uint32_t lead, uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\t"
+               "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n\t"
+               "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "r"(lead) : "memory");
+}
 __device__ __forceinline__ float tf32_rna(float v) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -127,7 +158,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
 
 struct PmiTcDev {
   const float *w0, *b0, *b1, *w2;  // [384*5] [384] [128] [128] folded fp32
-  const float *w1_tiles;           // [12][2][128 x 32] fc1 pre-split (hi | lo) in the UMMA layout
+  const float *w1_tiles;           // [48][2][128 x 8] fc1 pre-split (hi | lo) in the UMMA layout
   float b2;
 };
 
@@ -136,24 +167,23 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
                      int G, double coop, double *__restrict__ stats_partial) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int n = P.n, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool producer = warp > 0;
+  const bool producer = warp >= 1 && warp <= TC_NP / 32;   // warp 0 = MMA issue, last warp = weight loader
   // producers: hardware warp w may only touch TMEM lanes 32*(w%4)..+31, so rows follow the warp id
-  const int row = 32 * (warp & 3) + lane, part_id = (warp - 1) >> 2, pt = tid - 32;
+  const int row = 32 * (warp & 3) + lane, mytile = (warp - 1) >> 2, pt = tid - 32;
   float *s_obs = reinterpret_cast<float *>(smem + TcSmem::obs);
   double *s_raw = reinterpret_cast<double *>(smem + TcSmem::raw);
   uint64_t *s_nbr = reinterpret_cast<uint64_t *>(smem + TcSmem::nbr);
   uint32_t *s_off = reinterpret_cast<uint32_t *>(smem + TcSmem::off);
   float *s_logit = reinterpret_cast<float *>(smem + TcSmem::logit);
   float *s_w0 = reinterpret_cast<float *>(smem + TcSmem::w0);
-  float *s_part = reinterpret_cast<float *>(smem + TcSmem::part);
   float *s_b1 = reinterpret_cast<float *>(smem + TcSmem::b1);
   float *s_w2 = reinterpret_cast<float *>(smem + TcSmem::w2);
   double *s_red = reinterpret_cast<double *>(smem + TcSmem::red);
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + TcSmem::bar + 88);
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + TcSmem::bar + 120);
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + TcSmem::bar;
-  // [s] = stage, [a] = accumulator
-  const uint32_t bar_bfull = bar0, bar_aready = bar0 + 16, bar_free = bar0 + 32, bar_accfull = bar0 + 48, bar_accfree = bar0 + 64;
+  const uint32_t bar_bfull = bar0, bar_aready = bar0 + 8 * TC_NS, bar_free = bar0 + 16 * TC_NS;  // [TC_NS]: one per stage
+  const uint32_t bar_accfull = bar0 + 24 * TC_NS, bar_accfree = bar_accfull + 8;               // one each: the set's accumulators
 
   for (int k = tid; k < TC_H3 * 8; k += TC_NT) {  // per unit: {bias, w0..w4, 0, 0} -> two 128-bit broadcast loads
     const int u = k >> 3, e = k & 7;
@@ -161,17 +191,17 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
   }
   for (int k = tid; k < TC_H; k += TC_NT) { s_b1[k] = W.b1[k]; s_w2[k] = W.w2[k]; }
   if (tid == 0) {
-    for (int k = 0; k < 2; k++) {
-      mbar_init(bar_bfull + 8 * k, 1);         // expect_tx by the control lane + TMA bytes
-      mbar_init(bar_aready + 8 * k, 4 * TC_Q);       // one arrive per producer warp
-      mbar_init(bar_free + 8 * k, 1);          // tcgen05.commit
-      mbar_init(bar_accfull + 8 * k, 1);       // tcgen05.commit
-      mbar_init(bar_accfree + 8 * k, 4 * TC_Q);      // one arrive per producer warp
+    for (int k = 0; k < TC_NS; k++) {
+      mbar_init(bar_bfull + 8 * k, 1);              // expect_tx by the control lane + TMA bytes
+      mbar_init(bar_aready + 8 * k, TC_NP / 32);    // one arrive per producer warp
+      mbar_init(bar_free + 8 * k, 1);               // tcgen05.commit
     }
+    mbar_init(bar_accfull, 1);                      // tcgen05.commit
+    mbar_init(bar_accfree, TC_NP / 32);             // one arrive per producer warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {  // tensor memory: two 128-column fp32 accumulators, allocated by one warp
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(256u) : "memory");
+  if (warp == 0) {  // all of tensor memory: four 128-column fp32 accumulators, allocated by one warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -179,8 +209,11 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *s_tmem;
 
-  uint32_t g = 0;   // K-chunks processed so far by this CTA (stage = g & 1, use = g >> 1): same sequence on both sides
-  uint32_t t = 0;   // tiles processed so far (accumulator = t & 1, use = t >> 1)
+  // Static ring schedule: a set is TC_NCHUNK = 48 chunks and the ring has TC_NS = 4 stages, so chunk c of every set
+  // uses stage c % 4 and it is that stage's (12 * set + c / 4)-th use: the mbarrier phase parity is (c / 4) & 1 in
+  // every set, and all shared-memory addresses and descriptors are compile-time offsets from the base.
+  static_assert(TC_NCHUNK % (2 * TC_NS) == 0, "ring schedule assumes an even number of ring turns per set");
+  uint32_t t = 0;   // sets processed so far by this CTA (phase of the accumulator barriers); same sequence in all roles
   const int64_t ngroups = (env_count + G - 1) / G;
   double st_r = 0;
 
@@ -197,7 +230,7 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
       s_off[a + 1] = __popcll(n0) + __popcll(n1);
     }
     __syncthreads();
-    if (warp == 1) {  // exclusive scan of the neighbour counts (A <= 512): 16 per lane + warp scan
+    if (warp == 1) {  // exclusive scan of the neighbour counts (A <= 256): 8 per lane + warp scan
       const int per = (A + 31) / 32, lo = lane * per;
       uint32_t sum = 0;
       for (int k = 0; k < per; k++) if (lo + k < A) sum += s_off[lo + k + 1];
@@ -210,82 +243,68 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
     __syncthreads();
     const int npairs = (int)s_off[A];
     const int ntiles = (npairs + 127) / 128;
+    const int nsets = (ntiles + TC_SET - 1) / TC_SET;
 
-    if (!producer) {
-      // =============================== control warp: TMA + MMA issue ===============================
-      if (lane == 0) {
-        // fc1 chunk c into the stage of chunk number gg (the MMAs that last read that stage must be done)
-        auto load_b = [&](const uint32_t gg, const int c) {
-          const uint32_t s = gg & 1, use = gg >> 1;
-          if (use > 0) mbar_wait(bar_free + 8 * s, (use - 1) & 1);
-          mbar_expect_tx(bar_bfull + 8 * s, 2 * TC_TILE_BYTES);
-          bulk_g2s(sbase + TcSmem::stage + s * 4u * TC_TILE_BYTES + 2 * TC_TILE_BYTES,
-                   W.w1_tiles + (size_t)c * (2 * TC_TILE_BYTES / 4), 2 * TC_TILE_BYTES, bar_bfull + 8 * s);
-        };
-        if (ntiles > 0) load_b(g, 0);
-        for (int tile = 0; tile < ntiles; tile++, t++) {
-          const uint32_t acc = t & 1, d_tmem = tmem_d + 128u * acc;
-          for (int c = 0; c < TC_NCHUNK; c++, g++) {
-            const uint32_t s = g & 1, use = g >> 1;
-            const uint32_t stage = sbase + TcSmem::stage + s * 4u * TC_TILE_BYTES;
-            if (c == 0 && (t >> 1) > 0) mbar_wait(bar_accfree + 8 * acc, ((t >> 1) - 1) & 1);  // epilogue of tile t-2 done
-            mbar_wait(bar_aready + 8 * s, use & 1);  // producers have written A
-            mbar_wait(bar_bfull + 8 * s, use & 1);   // weights have landed
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t ah = stage, al = stage + TC_TILE_BYTES, bh = stage + 2 * TC_TILE_BYTES, bl = stage + 3 * TC_TILE_BYTES;
+    if (warp == 0) {
+      // =============================== MMA warp ===============================
+      const uint32_t lead = elect_one();
+      const int u_nsets = __shfl_sync(0xffffffffu, nsets, 0), u_ntiles = __shfl_sync(0xffffffffu, ntiles, 0);
+      const uint32_t u_tmem = __shfl_sync(0xffffffffu, tmem_d, 0);
+      for (int set = 0; set < u_nsets; set++, t++) {
+        const int nts = min(TC_SET, u_ntiles - set * TC_SET);
+        if (t > 0) mbar_wait(bar_accfree, (t - 1) & 1);  // epilogue of the previous set done
+#pragma unroll 1
+        for (int c4 = 0; c4 < TC_NCHUNK / TC_NS; c4++) {
+          const uint32_t par = c4 & 1;
 #pragma unroll
-            for (int ks = 0; ks < TC_KC / 8; ks++) {  // one MMA consumes K = 8 = two 16-byte core-matrix columns
-              const uint32_t o = (uint32_t)ks * 2u * 2048u;
-              umma_tf32(d_tmem, umma_desc(ah + o), umma_desc(bh + o), (c | ks) ? 1u : 0u);
+          for (int s = 0; s < TC_NS; s++) {
+            const uint32_t stage = sbase + TcSmem::stage + s * TC_STAGE_BYTES;
+            mbar_wait(bar_aready + 8 * s, par);  // producers have written A
+            mbar_wait(bar_bfull + 8 * s, par);   // weights have landed
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // descriptors differ only in the 14-bit address field: add (byte offset >> 4) to the low word
+            const uint64_t dbh = umma_desc(stage + 2 * TC_SET * TC_A_BYTES), dbl = dbh + (TC_A_BYTES >> 4);
+            const uint64_t da0 = umma_desc(stage);
+            const uint32_t acc = (c4 | s) ? 1u : 0u;
+#pragma unroll
+            for (int q = 0; q < TC_SET; q++) {
+              if (q < nts) {
+                const uint64_t dah = da0 + (uint64_t)(q * 2 * (TC_A_BYTES >> 4)), dal = dah + (TC_A_BYTES >> 4);
+                const uint32_t d_tmem = u_tmem + 128u * (uint32_t)q;
+                umma_tf32_p(lead, d_tmem, dah, dbh, acc);
 #ifndef TC_ABL_MMA1
-              umma_tf32(d_tmem, umma_desc(al + o), umma_desc(bh + o), 1u);
-              umma_tf32(d_tmem, umma_desc(ah + o), umma_desc(bl + o), 1u);
+                umma_tf32_p(lead, d_tmem, dal, dbh, 1u);
+                umma_tf32_p(lead, d_tmem, dah, dbl, 1u);
 #endif
+              }
             }
-            umma_commit(bar_free + 8 * s);                              // stage reusable when these MMAs are done
-            if (c == TC_NCHUNK - 1) umma_commit(bar_accfull + 8 * acc);  // accumulator complete
-            // weights of the next chunk stream in behind the MMAs just queued
-            if (c + 1 < TC_NCHUNK) load_b(g + 1, c + 1);
-            else if (tile + 1 < ntiles) load_b(g + 1, 0);
+            umma_commit_p(lead, bar_free + 8 * s);  // stage reusable when these MMAs are done
+          }
+        }
+        umma_commit_p(lead, bar_accfull);  // accumulators complete
+      }
+    } else if (!producer) {
+      // =============================== weight loader warp ===============================
+      const uint32_t lead = elect_one();
+      const int u_nsets = __shfl_sync(0xffffffffu, nsets, 0);
+      for (int set = 0; set < u_nsets; set++, t++) {
+#pragma unroll 1
+        for (int c4 = 0; c4 < TC_NCHUNK / TC_NS; c4++) {
+#pragma unroll
+          for (int s = 0; s < TC_NS; s++) {
+            if (t > 0 || c4 > 0) mbar_wait(bar_free + 8 * s, (c4 & 1) ^ 1);  // the MMAs of the previous use are done
+            load_chunk_p(lead, sbase + TcSmem::stage + s * TC_STAGE_BYTES + 2 * TC_SET * TC_A_BYTES,
+                         W.w1_tiles + (size_t)(c4 * TC_NS + s) * (2 * TC_A_BYTES / 4), 2 * TC_A_BYTES, bar_bfull + 8 * s);
           }
         }
       }
-      __syncwarp();
     } else {
       // =============================== producers: rows, layer 0, epilogue ===============================
-      // epilogue of tile number `tt` (rows p0e..): bias + ReLU + fc2 (PMINet.py:59-62); the two threads of a row take
-      // 64 accumulator columns each.  It runs one tile late, after the first two chunks of the next tile have been
-      // produced, so the tensor pipe always has work queued while the accumulator is drained.
-      auto epilogue = [&](const uint32_t tt, const int p0e) {
-        const uint32_t acc_i = tt & 1;
-        mbar_wait(bar_accfull + 8 * acc_i, (tt >> 1) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float part = 0.f;
-#pragma unroll 1
-        for (int cb = part_id * (128 / TC_Q); cb < (part_id + 1) * (128 / TC_Q); cb += 32) {
-          float v[32];
-          tmem_ld32(tmem_d + 128u * acc_i + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)cb, v);
-#pragma unroll
-          for (int k = 0; k < 32; k++) part = fmaf(s_w2[cb + k], fmaxf(v[k] + s_b1[cb + k], 0.f), part);
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_accfree + 8 * acc_i);  // this warp's rows have left tensor memory
-        // combine the two halves of each row (producer-only named barrier: warp 0 is busy issuing MMAs)
-        if (part_id) s_part[(part_id - 1) * 128 + row] = part;
-        asm volatile("bar.sync 1, %0;" ::"n"(TC_NP) : "memory");
-        if (!part_id && p0e + row < npairs) {
-          if (TC_Q == 4) s_logit[p0e + row] = ((part + s_part[row]) + (s_part[128 + row] + s_part[256 + row])) + W.b2;
-          else s_logit[p0e + row] = (part + s_part[row]) + W.b2;
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(TC_NP) : "memory");
-      };
-
-      for (int tile = 0; tile < ntiles; tile++, t++) {
-        const int p0 = tile * 128;
-        // ---- this thread's pair row: flat index -> (UAV a, its k-th neighbour b), x = la_a * la_b (uav.py:280-281)
+      for (int set = 0; set < nsets; set++, t++) {
+        const int p = (set * TC_SET + mytile) * 128 + row;   // this thread's pair row
+        const bool live = set * TC_SET + mytile < ntiles;    // warp-uniform: the tile exists
+        // ---- flat pair index -> (UAV a, its k-th neighbour b), x = la_a * la_b (uav.py:280-281)
         float x[12];
-        const int p = p0 + row;
         if (p < npairs) {
           int lo = 0, hi = A;  // largest a with off[a] <= p
           while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= (uint32_t)p) lo = mid; else hi = mid; }
@@ -304,60 +323,74 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
           for (int q = 0; q < 12; q++) x[q] = 0.f;
         }
 
-        // ---- layer 0 per K-chunk of 32 hidden units into the stage ring.  The three input branches
+        // ---- layer 0 per K-chunk of 8 hidden units into the stage ring.  The three input branches
         //      (communication 5, observation 4, boundary/state 3 inputs; PMINet.py:45-58, BN folded) are unrolled
-        //      so the row stays in registers; each branch covers 4 chunks.
+        //      so the row stays in registers; each branch covers 16 chunks.
         auto run_chunk = [&](const int c, const float *xin, const int dim) {
-          const uint32_t s = g & 1, use = g >> 1;
-          if (use > 0) {  // MMAs that read this stage have completed
-            mbar_wait(bar_free + 8 * s, (use - 1) & 1);
+          const uint32_t s = c % TC_NS, c4 = c / TC_NS;
+          if (t > 0 || c4 > 0) {  // MMAs that read this stage have completed
+            mbar_wait(bar_free + 8 * s, (c4 & 1) ^ 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           }
-          unsigned char *a_hi = smem + TcSmem::stage + (size_t)s * 4 * TC_TILE_BYTES, *a_lo = a_hi + TC_TILE_BYTES;
+          unsigned char *a_hi = smem + TcSmem::stage + (size_t)s * TC_STAGE_BYTES + (size_t)mytile * 2 * TC_A_BYTES;
+          unsigned char *a_lo = a_hi + TC_A_BYTES;
 #ifdef TC_ABL_NOPROD
           if (c < 0)
 #endif
+          if (live) {
 #pragma unroll 2
-          for (int gq = part_id * (8 / TC_Q); gq < (part_id + 1) * (8 / TC_Q); gq++) {  // this thread's share of the chunk
-            float hv[4], lv[4];
+            for (int gq = 0; gq < TC_KC / 4; gq++) {
+              float hv[4], lv[4];
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-              const int u = c * TC_KC + gq * 4 + e;
-              const float4 wa = *reinterpret_cast<const float4 *>(s_w0 + u * 8);      // bias, w0, w1, w2
-              const float4 wb = *reinterpret_cast<const float4 *>(s_w0 + u * 8 + 4);  // w3, w4, 0, 0
-              float acc = wa.x;
-              acc = fmaf(wa.y, xin[0], acc);
-              acc = fmaf(wa.z, xin[1], acc);
-              acc = fmaf(wa.w, xin[2], acc);
-              if (dim > 3) acc = fmaf(wb.x, xin[3], acc);
-              if (dim > 4) acc = fmaf(wb.y, xin[4], acc);
-              acc = fmaxf(acc, 0.f);
-              hv[e] = tf32_rna(acc);
-              lv[e] = tf32_rna(acc - hv[e]);
+              for (int e = 0; e < 4; e++) {
+                const int u = c * TC_KC + gq * 4 + e;
+                const float4 wa = *reinterpret_cast<const float4 *>(s_w0 + u * 8);      // bias, w0, w1, w2
+                const float4 wb = *reinterpret_cast<const float4 *>(s_w0 + u * 8 + 4);  // w3, w4, 0, 0
+                float acc = wa.x;
+                acc = fmaf(wa.y, xin[0], acc);
+                acc = fmaf(wa.z, xin[1], acc);
+                acc = fmaf(wa.w, xin[2], acc);
+                if (dim > 3) acc = fmaf(wb.x, xin[3], acc);
+                if (dim > 4) acc = fmaf(wb.y, xin[4], acc);
+                acc = fmaxf(acc, 0.f);
+                hv[e] = tf32_rna(acc);
+                lv[e] = tf32_rna(acc - hv[e]);
+              }
+              *reinterpret_cast<float4 *>(a_hi + gq * 2048 + row * 16) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+              *reinterpret_cast<float4 *>(a_lo + gq * 2048 + row * 16) = make_float4(lv[0], lv[1], lv[2], lv[3]);
             }
-            *reinterpret_cast<float4 *>(a_hi + gq * 2048 + row * 16) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-            *reinterpret_cast<float4 *>(a_lo + gq * 2048 + row * 16) = make_float4(lv[0], lv[1], lv[2], lv[3]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
           }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_aready + 8 * s);
-          g++;
         };
 #pragma unroll 1
-        for (int cc = 0; cc < 2; cc++) run_chunk(cc, x, 5);
-        if (tile > 0) epilogue(t - 1, p0 - 128);
+        for (int cc = 0; cc < 16; cc++) run_chunk(cc, x, 5);
 #pragma unroll 1
-        for (int cc = 2; cc < 4; cc++) run_chunk(cc, x, 5);
+        for (int cc = 16; cc < 32; cc++) run_chunk(cc, x + 5, 4);
 #pragma unroll 1
-        for (int cc = 4; cc < 8; cc++) run_chunk(cc, x + 5, 4);
+        for (int cc = 32; cc < 48; cc++) run_chunk(cc, x + 9, 3);
+
+        // ---- epilogue: bias + ReLU + fc2 (PMINet.py:59-62) over the row's 128 accumulator columns
+        mbar_wait(bar_accfull, t & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (live) {
+          float part = 0.f;
 #pragma unroll 1
-        for (int cc = 8; cc < 12; cc++) run_chunk(cc, x + 9, 3);
+          for (int cb = 0; cb < 128; cb += 32) {
+            float v[32];
+            tmem_ld32(tmem_d + 128u * (uint32_t)mytile + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)cb, v);
+#pragma unroll
+            for (int k = 0; k < 32; k++) part = fmaf(s_w2[cb + k], fmaxf(v[k] + s_b1[cb + k], 0.f), part);
+          }
+          if (p < npairs) s_logit[p] = part + W.b2;
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_accfree);  // this warp's rows have left tensor memory
       }
-      if (ntiles > 0) epilogue(t - 1, (ntiles - 1) * 128);
     }
     __syncthreads();
-    // the control lane advanced g and t privately; publish them to its warp (the producers counted on their own)
-    if (!producer) { g = __shfl_sync(0xffffffffu, g, 0); t = __shfl_sync(0xffffffffu, t, 0); }
 
     // ---- softmax over each UAV's neighbours (scipy.special.softmax on float32) and the mix (uav.py:284-290)
     if (producer) {
@@ -394,6 +427,6 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
     }
   }
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(256u) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512u) : "memory");
   block_stats_commit(s_red, stats_partial + (size_t)blockIdx.x * STAT_W, st_r, 0, 0, 0, 0, 0, 0, TC_NT);
 }

@@ -399,7 +399,7 @@ extern "C" int uavsim_set_pmi_weights(uavsim_t *h, const UavSimPmiWeights *w, vo
   if (H == TC_H) {
     // tensor-core path: fc1 split hi/lo (TF32) and laid out as the K-major UMMA tiles the kernel bulk-copies:
     // chunk c, part {hi, lo}, element (unit o, input k) at float (k/4)*512 + o*4 + (k%4)
-    const size_t tile = TC_TILE_BYTES / 4, total_t = (size_t)TC_NCHUNK * 2 * tile;
+    const size_t tile = TC_A_BYTES / 4, total_t = (size_t)TC_NCHUNK * 2 * tile;
     float *tiles = (float *)malloc(total_t * sizeof(float));
     for (int c = 0; c < TC_NCHUNK; c++)
       for (int o = 0; o < TC_H; o++)
