@@ -53,8 +53,8 @@ struct TcSmem {  // byte offsets inside dynamic shared memory (base is 1024-byte
   static constexpr uint32_t nbr = raw + TC_AMAX * 8;                     // uint64 [AMAX*2]
   static constexpr uint32_t off = nbr + TC_AMAX * 16;                    // uint32 [AMAX+4]
   static constexpr uint32_t logit = off + (TC_AMAX + 4) * 4;             // float [PMAX]
-  static constexpr uint32_t w0 = logit + TC_PMAX * 4;                    // float [384*8]: bias, 5 weights, 2 pad per unit
-  static constexpr uint32_t b1 = w0 + TC_H3 * 8 * 4;                     // float [128]
+  static constexpr uint32_t w0 = logit + TC_PMAX * 4;                    // float [192*12]: per unit pair, bias and 5 weights interleaved
+  static constexpr uint32_t b1 = w0 + (TC_H3 / 2) * 12 * 4;                    // float [128]
   static constexpr uint32_t w2 = b1 + TC_H * 4;                          // float [128]
   static constexpr uint32_t red = w2 + TC_H * 4;                         // double [7 per warp]
   static constexpr uint32_t bar = red + (TC_NT / 32) * 7 * 8;            // 3 x TC_NS + 2 mbarriers + tmem pointer
@@ -73,18 +73,20 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// bounded wait: a barrier that never completes (a descriptor bug) traps instead of hanging the GPU
+// bounded wait: a barrier that never completes (a descriptor bug) traps instead of hanging the GPU.  The suspend-time
+// hint lets the hardware park the warp until the phase completes instead of re-polling: spinning producers would
+// otherwise take issue slots from the MMA warp and from the producers that still have work.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   for (uint32_t spin = 0; !done; spin++) {
     asm volatile(
         "{\n\t.reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, P1;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(20000u)
         : "memory");
-    if (spin > (1u << 26)) __trap();
+    if (spin > (1u << 22)) __trap();
   }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
@@ -137,10 +139,18 @@ __device__ __forceinline__ void load_chunk_p(uint32_t lead, uint32_t dst, const 
                "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "r"(lead) : "memory");
 }
+// round to TF32 (10 mantissa bits), nearest with ties away from zero like cvt.rna.tf32.f32, for finite inputs: two
+// integer instructions (the cvt expands to an inf/nan test plus the same arithmetic)
 __device__ __forceinline__ float tf32_rna(float v) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+}
+__device__ __forceinline__ uint64_t tc_pack2(float lo, float hi) {
+  return (uint64_t)__float_as_uint(lo) | ((uint64_t)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ uint64_t tc_fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
   uint32_t *u = reinterpret_cast<uint32_t *>(v);
@@ -185,9 +195,9 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
   const uint32_t bar_bfull = bar0, bar_aready = bar0 + 8 * TC_NS, bar_free = bar0 + 16 * TC_NS;  // [TC_NS]: one per stage
   const uint32_t bar_accfull = bar0 + 24 * TC_NS, bar_accfree = bar_accfull + 8;               // one each: the set's accumulators
 
-  for (int k = tid; k < TC_H3 * 8; k += TC_NT) {  // per unit: {bias, w0..w4, 0, 0} -> two 128-bit broadcast loads
-    const int u = k >> 3, e = k & 7;
-    s_w0[k] = (e == 0) ? W.b0[u] : (e <= 5 ? W.w0[u * 5 + e - 1] : 0.f);
+  for (int k = tid; k < (TC_H3 / 2) * 12; k += TC_NT) {  // unit pair j: {b, b', w0, w0', .. w4, w4'} -> three 128-bit loads
+    const int u = 2 * (k / 12) + (k & 1), e = (k % 12) >> 1;
+    s_w0[k] = (e == 0) ? W.b0[u] : W.w0[u * 5 + e - 1];
   }
   for (int k = tid; k < TC_H; k += TC_NT) { s_b1[k] = W.b1[k]; s_w2[k] = W.w2[k]; }
   if (tid == 0) {
@@ -323,10 +333,14 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
           for (int q = 0; q < 12; q++) x[q] = 0.f;
         }
 
+        uint64_t xx[12];  // {x, x}: the broadcast operand of the packed FMAs
+#pragma unroll
+        for (int q = 0; q < 12; q++) xx[q] = tc_pack2(x[q], x[q]);
+
         // ---- layer 0 per K-chunk of 8 hidden units into the stage ring.  The three input branches
         //      (communication 5, observation 4, boundary/state 3 inputs; PMINet.py:45-58, BN folded) are unrolled
         //      so the row stays in registers; each branch covers 16 chunks.
-        auto run_chunk = [&](const int c, const float *xin, const int dim) {
+        auto run_chunk = [&](const int c, const uint64_t *xin, const int dim) {
           const uint32_t s = c % TC_NS, c4 = c / TC_NS;
           if (t > 0 || c4 > 0) {  // MMAs that read this stage have completed
             mbar_wait(bar_free + 8 * s, (c4 & 1) ^ 1);
@@ -338,23 +352,25 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
           if (c < 0)
 #endif
           if (live) {
-#pragma unroll 2
+#pragma unroll
             for (int gq = 0; gq < TC_KC / 4; gq++) {
               float hv[4], lv[4];
 #pragma unroll
-              for (int e = 0; e < 4; e++) {
-                const int u = c * TC_KC + gq * 4 + e;
-                const float4 wa = *reinterpret_cast<const float4 *>(s_w0 + u * 8);      // bias, w0, w1, w2
-                const float4 wb = *reinterpret_cast<const float4 *>(s_w0 + u * 8 + 4);  // w3, w4, 0, 0
-                float acc = wa.x;
-                acc = fmaf(wa.y, xin[0], acc);
-                acc = fmaf(wa.z, xin[1], acc);
-                acc = fmaf(wa.w, xin[2], acc);
-                if (dim > 3) acc = fmaf(wb.x, xin[3], acc);
-                if (dim > 4) acc = fmaf(wb.y, xin[4], acc);
-                acc = fmaxf(acc, 0.f);
-                hv[e] = tf32_rna(acc);
-                lv[e] = tf32_rna(acc - hv[e]);
+              for (int e = 0; e < 4; e += 2) {  // two units per packed fp32 instruction (FFMA2)
+                const float4 *wp = reinterpret_cast<const float4 *>(s_w0 + ((c * TC_KC + gq * 4 + e) >> 1) * 12);
+                const float4 q0 = wp[0], q1 = wp[1];  // b b' w0 w0' | w1 w1' w2 w2'
+                uint64_t acc = tc_pack2(q0.x, q0.y);
+                acc = tc_fma2(tc_pack2(q0.z, q0.w), xin[0], acc);
+                acc = tc_fma2(tc_pack2(q1.x, q1.y), xin[1], acc);
+                acc = tc_fma2(tc_pack2(q1.z, q1.w), xin[2], acc);
+                if (dim > 3) {
+                  const float4 q2 = wp[2];            // w3 w3' | w4 w4'
+                  acc = tc_fma2(tc_pack2(q2.x, q2.y), xin[3], acc);
+                  if (dim > 4) acc = tc_fma2(tc_pack2(q2.z, q2.w), xin[4], acc);
+                }
+                const float a0 = fmaxf(__uint_as_float((uint32_t)acc), 0.f), a1 = fmaxf(__uint_as_float((uint32_t)(acc >> 32)), 0.f);
+                hv[e] = tf32_rna(a0); hv[e + 1] = tf32_rna(a1);
+                lv[e] = tf32_rna(a0 - hv[e]); lv[e + 1] = tf32_rna(a1 - hv[e + 1]);
               }
               *reinterpret_cast<float4 *>(a_hi + gq * 2048 + row * 16) = make_float4(hv[0], hv[1], hv[2], hv[3]);
               *reinterpret_cast<float4 *>(a_lo + gq * 2048 + row * 16) = make_float4(lv[0], lv[1], lv[2], lv[3]);
@@ -365,11 +381,11 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
           if (lane == 0) mbar_arrive(bar_aready + 8 * s);
         };
 #pragma unroll 1
-        for (int cc = 0; cc < 16; cc++) run_chunk(cc, x, 5);
+        for (int cc = 0; cc < 16; cc++) run_chunk(cc, xx, 5);
 #pragma unroll 1
-        for (int cc = 16; cc < 32; cc++) run_chunk(cc, x + 5, 4);
+        for (int cc = 16; cc < 32; cc++) run_chunk(cc, xx + 5, 4);
 #pragma unroll 1
-        for (int cc = 32; cc < 48; cc++) run_chunk(cc, x + 9, 3);
+        for (int cc = 32; cc < 48; cc++) run_chunk(cc, xx + 9, 3);
 
         // ---- epilogue: bias + ReLU + fc2 (PMINet.py:59-62) over the row's 128 accumulator columns
         mbar_wait(bar_accfull, t & 1);
