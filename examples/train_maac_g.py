@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""MAAC-G training on the GPU-resident batched environment (BASELINE.json configs[4]).
+"""MAAC / MAAC-G / MAAC-R training on the GPU-resident batched environment (BASELINE.json configs[4]).
 
     python examples/train_maac_g.py --envs 4096 --episodes 5
+    python examples/train_maac_g.py --envs 1024 --episodes 5 --method MAAC-R --replay     # PER + PMI training
     python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 examples/train_maac_g.py --envs 32768
 
 Environments are sharded over ranks (no data-path collective); gradients are all-reduced by DDP, episode
@@ -17,7 +18,8 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from marl_uavs_targets_tracking_b200 import BatchedEnvironment, default_config, shard_envs  # noqa: E402
-from marl_uavs_targets_tracking_b200.rollout import BatchedActorCritic, operate_epoch_batched  # noqa: E402
+from marl_uavs_targets_tracking_b200 import PMINetwork  # noqa: E402
+from marl_uavs_targets_tracking_b200.rollout import BatchedActorCritic, operate_epoch_batched, train_batched  # noqa: E402
 
 
 def main():
@@ -27,7 +29,10 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--n-uav", type=int, default=10)
     ap.add_argument("--m-targets", type=int, default=10)
-    ap.add_argument("--method", default="MAAC-G", choices=["MAAC", "MAAC-G"])
+    ap.add_argument("--method", default="MAAC-G", choices=["MAAC", "MAAC-G", "MAAC-R"])
+    ap.add_argument("--replay", action="store_true",
+                    help="reference loop: device prioritized replay + |TD| priorities (+ PMI training for MAAC-R)")
+    ap.add_argument("--buffer", type=int, default=1 << 22, help="replay capacity (transitions)")
     ap.add_argument("--minibatch", type=int, default=1 << 20, help="transitions per update")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -41,6 +46,19 @@ def main():
                              env_id_offset=offset, seed=cfg["seed"], num_steps=args.steps)
     torch.manual_seed(cfg["seed"])
     agent = BatchedActorCritic(12, 128, 12, 1e-4, 5e-4, 0.95, device, ddp=world > 1)  # src/configs/MAAC-G.yaml:30-36
+    pmi = PMINetwork(hidden_dim=128).to(device) if args.method == "MAAC-R" else None  # src/configs/MAAC-R.yaml:38-41
+    if args.replay or pmi is not None:
+        cfg.setdefault("actor_critic", {}).update(buffer_size=args.buffer, sample_size=min(args.minibatch, args.buffer))
+        cfg.setdefault("pmi", {}).setdefault("batch_size", 128)
+        t0 = time.perf_counter()
+
+        def report(ep, s):
+            if rank == 0:
+                print("episode %d  return %.4f  covered avg %.2f  actor %.4f critic %.4f%s  (%.1f s)" % (
+                    ep, s["return"], s["average_covered_targets"], s["actor_loss"], s["critic_loss"],
+                    "  pmi %.4f" % s["avg_pmi_loss"] if "avg_pmi_loss" in s else "", time.perf_counter() - t0))
+        train_batched(cfg, env, agent, pmi, args.episodes, args.steps, on_episode=report)
+        args.episodes = 0
     for ep in range(args.episodes):
         t0 = time.perf_counter()
         env.reset(cfg)

@@ -153,6 +153,45 @@ int uavsim_episode_stats(uavsim_t *h, double out[8], void *stream);
 int64_t uavsim_launch_count(const uavsim_t *h);
 int64_t uavsim_step_count(const uavsim_t *h);
 
+/* ------------------------------------------------------------------------------------------------
+ * Prioritized replay on the device -- PrioritizedReplayBuffer (src/train.py:73-139).
+ * The ring (states [C,D] f32, actions [C] i32, rewards [C] f32, next_states [C,D] f32, priorities [C] f32)
+ * lives in device memory owned by the handle; inputs and outputs are caller-owned DEVICE pointers.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct uavsim_replay uavsim_replay_t;
+
+/* PrioritizedReplayBuffer.__init__(capacity, alpha) (src/train.py:74-79) */
+int uavsim_replay_create(int64_t capacity, int state_dim, double alpha, int device, uavsim_replay_t **out);
+int uavsim_replay_destroy(uavsim_replay_t *h);
+
+/* add(transition_dict) (src/train.py:81-98): `count` transitions, each stored with the current maximum
+ * priority (1.0 while the buffer is empty); a batch longer than the capacity keeps its last `capacity` rows. */
+int uavsim_replay_add(uavsim_replay_t *h, const float *states, const int32_t *actions, const float *rewards,
+                      const float *next_states, int64_t count, void *stream);
+
+/* sample(batch_size, beta) (src/train.py:100-132): *n_out = min(batch, size) draws with replacement,
+ * P(i) = priority_i^alpha / sum, by inverse CDF like numpy.random.choice(p=...); weights (size*P(i))^-beta / max.
+ * `uniforms` = n_out doubles in [0,1) on the device, or NULL to draw them from Philox4x32-10 keyed
+ * (seed; sample index, counter). */
+int uavsim_replay_sample(uavsim_replay_t *h, int64_t batch, double beta, const double *uniforms, uint64_t seed,
+                         uint64_t counter, float *o_states, int32_t *o_actions, float *o_rewards, float *o_next_states,
+                         int64_t *o_indices, float *o_weights, int64_t *n_out, void *stream);
+
+/* update_priorities(indices, priorities) (src/train.py:134-136): sequential assignment, the last write to a
+ * repeated index wins. */
+int uavsim_replay_update_priorities(uavsim_replay_t *h, const int64_t *indices, const float *priorities,
+                                    int64_t count, void *stream);
+
+/* size() (src/train.py:138-139), ring write position, kernels launched so far */
+int64_t uavsim_replay_size(const uavsim_replay_t *h);
+int64_t uavsim_replay_pos(const uavsim_replay_t *h);
+int64_t uavsim_replay_launch_count(const uavsim_replay_t *h);
+
+/* Checkpoint / inspection: copy slots [0, size) of the ring, all `capacity` priorities and the probabilities of
+ * the last sample call into HOST buffers (any may be NULL).  Synchronises `stream`. */
+int uavsim_replay_export(uavsim_replay_t *h, float *states, int32_t *actions, float *rewards, float *next_states,
+                         float *priorities, float *probabilities, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

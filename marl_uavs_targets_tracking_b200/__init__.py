@@ -7,5 +7,6 @@ from .environment import BatchedEnvironment, Environment, params_from_config  # 
 from .pmi import PMINetwork, fold_pmi  # noqa: F401
 from .distributed import shard_envs, reduce_episode_stats, episode_summary  # noqa: F401
 from .config import default_config  # noqa: F401
+from .replay import PrioritizedReplayBuffer  # noqa: F401
 
 __version__ = "0.1.0"

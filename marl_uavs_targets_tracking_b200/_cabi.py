@@ -58,6 +58,19 @@ SYMBOLS = {
     "uavsim_episode_stats": (C.c_int, [_H, C.POINTER(C.c_double), C.c_void_p]),
     "uavsim_launch_count": (C.c_int64, [_H]),
     "uavsim_step_count": (C.c_int64, [_H]),
+    # prioritized replay (src/train.py:73-139)
+    "uavsim_replay_create": (C.c_int, [C.c_int64, C.c_int, C.c_double, C.c_int, C.POINTER(_H)]),
+    "uavsim_replay_destroy": (C.c_int, [_H]),
+    "uavsim_replay_add": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "uavsim_replay_sample": (C.c_int, [_H, C.c_int64, C.c_double, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.POINTER(C.c_int64), C.c_void_p]),
+    "uavsim_replay_update_priorities": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "uavsim_replay_size": (C.c_int64, [_H]),
+    "uavsim_replay_pos": (C.c_int64, [_H]),
+    "uavsim_replay_launch_count": (C.c_int64, [_H]),
+    "uavsim_replay_export": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
 }
 
 _lib = None

@@ -15,6 +15,7 @@
 #include "pmi_kernel.cuh"
 #include "pmi_tc_kernel.cuh"
 #include "aux_kernels.cuh"
+#include "replay.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // host side

@@ -2,13 +2,16 @@
 
 `PMINetwork` has the reference's constructor, parameter names (`state_dict()` keys) and
 `forward` / `inference` semantics (src/models/PMINet.py:20-72), so checkpoints written by the
-reference's `PMINetwork.save` load here and vice versa.  Training (`train_pmi`,
-src/models/PMINet.py:74-100) is learner-side code and stays stock PyTorch in the reference;
-it is out of scope for this path.
+reference's `PMINetwork.save` load here and vice versa.  `train_pmi` (src/models/PMINet.py:74-100,
+SURVEY.md section 8f row f-3) keeps the reference's sampling rule, loss and optimizer but gathers the
+3 000 state pairs with one indexed load on whatever device the module lives on instead of a python
+loop; the environment picks the new weights up through `pmi_version`.
 
 `fold_pmi` turns any module / state dict with those names into the BN-folded fp32 arrays the
 CUDA path consumes (include/uavsim.h: UavSimPmiWeights).
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -34,6 +37,7 @@ class PMINetwork(nn.Module):
         self.fc1 = nn.Linear(hidden_dim * 3, hidden_dim)
         self.bn1 = nn.BatchNorm1d(hidden_dim)
         self.fc2 = nn.Linear(hidden_dim, 1)
+        self.optimizer = torch.optim.Adam(self.parameters(), lr=0.001)  # src/models/PMINet.py:39
 
     def forward(self, x):
         if isinstance(x, np.ndarray):
@@ -53,6 +57,47 @@ class PMINetwork(nn.Module):
             single_data = single_data.unsqueeze(0)
         with torch.no_grad():
             return self.forward(single_data).item()
+
+    @staticmethod
+    def pair_loss(output1, output2):
+        """CustomLoss (src/models/PMINet.py:10-17): mean(log(1 + e^-o1) + log(1 + e^o2))."""
+        return torch.mean(torch.log(1 + torch.exp(-output1)) + torch.log(1 + torch.exp(output2)))
+
+    def train_pmi(self, config, train_data, n_uav):
+        """One PMI update (src/models/PMINet.py:74-100).  train_data [timesteps*n_uav, 12]: `b2_size` draws of
+        (timestep, uav A, uav B) -- same `torch.randint` calls on the CPU generator as the reference, so a seeded run
+        selects the same rows -- then minibatches of config['pmi']['batch_size'] through Adam.  Returns the mean
+        |loss| like the reference.  Runs on the module's device; train_data may live anywhere."""
+        self.train()
+        dev = self.fc2.weight.device
+        timesteps = train_data.size(0) // n_uav
+        # (the reference's view() needs a multiple of n_uav rows; a ragged tail is dropped here instead of raising)
+        data = train_data[:timesteps * n_uav].view(timesteps, n_uav, 12).to(dev, torch.float32)
+        timestep_indices = torch.randint(low=0, high=timesteps, size=(self.b2_size,))
+        uav_indices = torch.randint(low=0, high=n_uav, size=(self.b2_size, 2))
+        selected = data[timestep_indices.to(dev)[:, None], uav_indices.to(dev)]  # [b2, 2, 12]
+        bs = config["pmi"]["batch_size"]
+        nb = self.b2_size // bs
+        total = torch.zeros((), device=dev, dtype=torch.float64)  # the reference sums python floats
+        for i in range(nb):
+            self.optimizer.zero_grad()
+            batch = selected[i * bs:(i + 1) * bs]
+            loss = self.pair_loss(self.forward(batch[:, 0]), self.forward(batch[:, 1]))
+            total = total + loss.detach().abs().double()
+            loss.backward()
+            self.optimizer.step()
+        return float(total / nb)  # one device->host sync per call instead of one per minibatch
+
+    def save(self, save_dir, epoch_i):
+        """Same file layout as the reference (src/models/PMINet.py:102-106)."""
+        torch.save({"model_state_dict": self.state_dict(), "optimizer_state_dict": self.optimizer.state_dict()},
+                   os.path.join(save_dir, "pmi", "pmi_weights_" + str(epoch_i) + ".pth"))
+
+    def load(self, path):
+        if path and os.path.exists(path):
+            checkpoint = torch.load(path, map_location=self.fc2.weight.device)
+            self.load_state_dict(checkpoint["model_state_dict"])
+            self.optimizer.load_state_dict(checkpoint["optimizer_state_dict"])
 
 
 def _as_state(pmi):

@@ -11,6 +11,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .distributed import episode_summary, reduce_episode_stats
+from .replay import PrioritizedReplayBuffer
 
 
 class PolicyNet(nn.Module):
@@ -100,3 +101,37 @@ def operate_epoch_batched(config, env, agent, pmi, num_steps, keep_transitions=T
     stats = reduce_episode_stats(env.episode_stats(), device=env.device)
     transitions = {k: torch.cat(v) for k, v in bufs.items()} if keep_transitions else None
     return transitions, episode_summary(stats, n)
+
+
+def train_batched(config, env, agent, pmi, num_episodes, num_steps, buffer=None, sample_size=None, on_episode=None):
+    """The reference's training loop (src/train.py:199-287) on device tensors: per episode reset, roll out every
+    environment, push the transitions into the device prioritized replay, draw `sample_size` of them by priority,
+    one actor-critic update, write |TD error| back as priorities, and for MAAC-R one `train_pmi` pass on the sampled
+    states (the environment picks the new PMI weights up on its next step).
+
+    buffer defaults to a PrioritizedReplayBuffer of config['actor_critic']['buffer_size']; sample_size to
+    config['actor_critic']['sample_size'] or, if that is not positive, to one episode of one environment
+    (n_uav * num_steps, src/train.py:217-220).  Returns the list of per-episode summaries (plus losses)."""
+    ac = config.get("actor_critic", {})
+    if buffer is None:
+        buffer = PrioritizedReplayBuffer(int(ac.get("buffer_size", 1 << 20)), device=env.device, seed=config.get("seed", 0))
+    if sample_size is None:
+        sample_size = int(ac.get("sample_size", 0))
+    if sample_size <= 0:
+        sample_size = env.n_uav * num_steps
+    history = []
+    for ep in range(num_episodes):
+        env.reset(config)
+        transitions, summary = operate_epoch_batched(config, env, agent, pmi.eval() if pmi is not None else None, num_steps)
+        buffer.add(transitions)
+        sample, indices, _ = buffer.sample(sample_size)
+        actor_loss, critic_loss, td = agent.update(sample["states"], sample["actions"], sample["rewards"],
+                                                   sample["next_states"])
+        buffer.update_priorities(indices, td.abs())
+        summary.update(actor_loss=float(actor_loss), critic_loss=float(critic_loss))
+        if pmi is not None:
+            summary["avg_pmi_loss"] = pmi.train_pmi(config, sample["states"], env.n_uav)
+        history.append(summary)
+        if on_episode is not None:
+            on_episode(ep, summary)
+    return history

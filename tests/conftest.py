@@ -18,7 +18,9 @@ def pytest_configure(config):
 
 
 def golden_names():
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """Environment fixtures (tests/golden/make_golden.py); learner_* come from make_learner_golden.py."""
+    names = (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    return sorted(n for n in names if not n.startswith("learner_"))
 
 
 def load_golden(name):

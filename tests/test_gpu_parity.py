@@ -350,6 +350,39 @@ def test_reference_shaped_api_single_env():
     env.close()
 
 
+def test_trace_files_have_the_reference_layout(tmp_path):
+    """Row f-4: `save_position` / `save_covered_num` write what src/environment.py:229-244 writes -- u_xy<k>.csv is the
+    (n_uav, steps, 2) array flattened to rows (UAV-major), header `x,y`; covered_target_num<k>.csv one count per step.
+    Replays a reference recording so the numbers are the reference's too."""
+    from marl_uavs_targets_tracking_b200 import Environment
+    g = load_golden("d10_mean_s42")
+    cfg = golden_config(g)
+    e = cfg["environment"]
+    env = Environment(n_uav=e["n_uav"], m_targets=e["m_targets"], x_max=e["x_max"], y_max=e["y_max"], na=e["na"])
+    env.reset(config=cfg)
+    env.set_state(cfg, *(torch.as_tensor(np.asarray(g[k + "0"])[None]) for k in ("ux", "uy", "uh", "ua", "tx", "ty", "th")))
+    T = 30
+    for t in range(T):
+        env.step(cfg, None, [int(a) for a in g["actions"][t]])
+    for d in ("u_xy", "t_xy", "covered_target_num"):
+        (tmp_path / d).mkdir()
+    env.save_position(str(tmp_path), 7)
+    env.save_covered_num(str(tmp_path), 7)
+    u = np.loadtxt(tmp_path / "u_xy" / "u_xy7.csv", delimiter=",", skiprows=1)
+    tt = np.loadtxt(tmp_path / "t_xy" / "t_xy7.csv", delimiter=",", skiprows=1)
+    c = np.loadtxt(tmp_path / "covered_target_num" / "covered_target_num7.csv", delimiter=",", skiprows=1)
+    assert open(tmp_path / "u_xy" / "u_xy7.csv").readline().strip() == "x,y"
+    assert open(tmp_path / "covered_target_num" / "covered_target_num7.csv").readline().strip() == "covered_target_num"
+    n, m = e["n_uav"], e["m_targets"]
+    ref_u = np.stack([g["ux"][:T], g["uy"][:T]], axis=-1).transpose(1, 0, 2).reshape(-1, 2)   # (n, T, 2) -> rows
+    ref_t = np.stack([g["tx"][:T], g["ty"][:T]], axis=-1).transpose(1, 0, 2).reshape(-1, 2)
+    assert u.shape == (n * T, 2) and tt.shape == (m * T, 2)
+    np.testing.assert_allclose(u, ref_u, rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(tt, ref_t, rtol=1e-12, atol=1e-9)
+    assert np.array_equal(c.astype(int), g["covered"][:T])
+    env.close()
+
+
 @pytest.mark.parametrize("n,m,E,method", [(10, 10, 4096, "MAAC"), (64, 64, 65536, "MAAC-G"), (10, 10, 16384, "MAAC-R")])
 def test_full_size_properties(n, m, E, method):
     """BASELINE.json sizes, size-independent properties: the second half of the batch is a copy of the
