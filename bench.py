@@ -267,6 +267,23 @@ def measure_workload(torch, dist, env_cls, args, name, rank, world, device, step
     res = {"name": name, "desc": desc, "n": n, "m": m, "E": E, "method": method, "ms": ms, "steps": steps,
            "launches": launches, "clocks": clocks, "value": E * world * n * steps / (ms * 1e-3), "trace": trace}
 
+    # the same random-policy rollout queued from C (uavsim_run_random_policy: action draw + step per iteration, no
+    # interpreter between steps): what a small batch needs, where one step is shorter than a Python-level call
+    env.reset(cfg)
+    env.run_random_policy(cfg, pmi, 4242, 0, warmup)
+    barrier()
+    ev0.record(torch.cuda.current_stream(device))
+    env.run_random_policy(cfg, pmi, 4242, warmup, steps)
+    ev1.record(torch.cuda.current_stream(device))
+    barrier()
+    ms_loop = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms_loop], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_loop = float(t.item())
+    res["device_loop"] = {"value": E * world * n * steps / (ms_loop * 1e-3), "unit": "agent-steps/s",
+                          "ms_per_step": ms_loop / steps, "api": "uavsim_run_random_policy (actions drawn on the device)"}
+
     if with_e2e:
         NH = min(NB, e2e_steps + 2)
         h_act = torch.empty((NH, E, n), dtype=torch.int32).pin_memory()
@@ -294,6 +311,46 @@ def measure_workload(torch, dist, env_cls, args, name, rank, world, device, step
     # the one collective of the path: episode statistics (<= 8 doubles), outside the timed region
     from marl_uavs_targets_tracking_b200 import reduce_episode_stats
     res["episode_stats"] = reduce_episode_stats(env.episode_stats(), device=device)
+    env.close()
+    return res
+
+
+def measure_training(torch, dist, env_cls, rank, world, device, steps=25, envs=65536):
+    """BASELINE configs[4]: MAAC-G rollout with the GPU-resident environment feeding the torch actor / critic
+    (one [E*n,12] actor forward + on-device categorical sample + one step launch per step), then the reference loop's
+    replay add / prioritized sample / actor-critic update / priority write-back (src/train.py:232-262)."""
+    from marl_uavs_targets_tracking_b200 import PrioritizedReplayBuffer, default_config
+    from marl_uavs_targets_tracking_b200.rollout import BatchedActorCritic, operate_epoch_batched
+    n = m = 10
+    cfg = default_config("MAAC-G", n, m)
+    env = env_cls(n, m, 2000, 2000, 12, n_envs=envs, device=device, env_id_offset=rank * envs, seed=42, num_steps=steps)
+    torch.manual_seed(42)
+    agent = BatchedActorCritic(12, 128, 12, 1e-4, 5e-4, 0.95, device, ddp=world > 1)
+    buf = PrioritizedReplayBuffer(1 << 24, device=device, seed=42)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    res = {}
+    for it in range(2):  # first pass warms the allocator and cuBLAS up
+        env.reset(cfg)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+        ev[0].record()
+        tr, summary = operate_epoch_batched(cfg, env, agent, None, steps)
+        ev[1].record()
+        buf.add(tr)
+        sample, idx, _ = buf.sample(1 << 20)
+        a_loss, c_loss, td = agent.update(sample["states"], sample["actions"], sample["rewards"], sample["next_states"])
+        buf.update_priorities(idx, td.abs())
+        ev[2].record()
+        torch.cuda.synchronize(device)
+        t = torch.tensor([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res = {"value": envs * world * n * steps / (float(t[0]) * 1e-3), "unit": "agent-steps/s (rollout incl. policy)",
+               "rollout_ms_per_step": float(t[0]) / steps, "learn_ms": float(t[1]), "envs_per_gpu": envs, "n_uav": n,
+               "m_targets": m, "method": "MAAC-G", "steps": steps, "update_batch": 1 << 20,
+               "replay_launches": buf.launches, "return": summary["return"]}
+        del tr, sample
     env.close()
     return res
 
@@ -343,7 +400,9 @@ def main():
                                  min(args.steps, 100), 5, False, 0)
             extras[name] = {"value": r["value"], "unit": "agent-steps/s", "ms_per_step": r["ms"] / r["steps"],
                             "envs_per_gpu": r["E"], "n_uav": r["n"], "m_targets": r["m"], "method": r["method"],
+                            "device_loop": r["device_loop"],
                             "roofline_frac": r["value"] / world * alg_bytes_per_env_step(r["n"], r["m"]) / r["n"] / (hbm_peak()[0] * 1e9)}
+        extras["train_maac_g"] = measure_training(torch, dist, BatchedEnvironment, rank, world, device)
 
     if rank == 0:
         n, m, E = main_res["n"], main_res["m"], main_res["E"]
@@ -370,6 +429,7 @@ def main():
                             "traffic": traffic, "peak_source": peak_src, "kernel": "uavsim_step_kernel",
                             "bytes_per_launch": bytes_per_launch,
                             "bytes_per_agent_step": alg_bytes_per_env_step(n, m) / n},
+               "device_loop": main_res["device_loop"],
                "episode_stats": main_res["episode_stats"], "other_workloads": extras}
         if main_res.get("trace"):
             out["ms_per_step_trace"] = {"every": args.trace_every, "ms": main_res["trace"]}

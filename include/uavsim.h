@@ -126,6 +126,11 @@ int uavsim_random_actions(uavsim_t *h, uint64_t seed, int64_t step, void *stream
 /* Environment.step (src/environment.py:120-164) for all E environments, device buffers. */
 int uavsim_step(uavsim_t *h, int mode, double cooperative, void *stream);
 
+/* nsteps x (uavsim_random_actions(seed, first_step + k); uavsim_step) queued on `stream` without returning to the
+ * caller in between: the random-policy rollout of BASELINE configs[1].  Outputs hold the last step's values. */
+int uavsim_run_random_policy(uavsim_t *h, int mode, double cooperative, uint64_t seed, int64_t first_step,
+                             int64_t nsteps, void *stream);
+
 /* Same, host buffers (pinned for real overlap): copies h_actions [E,n] in, steps, copies obs [E,n,12],
  * rew4 [4,E,n], covered [E] out, pipelined over `chunks` env ranges.  Blocks until the outputs are in
  * host memory.  Any output pointer may be NULL (skipped). */

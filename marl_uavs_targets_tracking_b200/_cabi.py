@@ -50,6 +50,7 @@ SYMBOLS = {
     "uavsim_begin_episode": (C.c_int, [_H, C.c_void_p]),
     "uavsim_random_actions": (C.c_int, [_H, C.c_uint64, C.c_int64, C.c_void_p]),
     "uavsim_step": (C.c_int, [_H, C.c_int, C.c_double, C.c_void_p]),
+    "uavsim_run_random_policy": (C.c_int, [_H, C.c_int, C.c_double, C.c_uint64, C.c_int64, C.c_int64, C.c_void_p]),
     "uavsim_step_host": (C.c_int, [_H, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_int, C.c_void_p]),
     "uavsim_set_reward_weights": (C.c_int, [_H, C.c_double, C.c_double, C.c_double]),

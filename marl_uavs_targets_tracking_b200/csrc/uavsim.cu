@@ -459,6 +459,23 @@ extern "C" int uavsim_step(uavsim_t *h, int mode, double coop, void *stream) {
   return launch_step_range(h, mode, coop, 0, h->E, done, (cudaStream_t)stream);
 }
 
+// Random-policy rollout without a host round trip per step (BASELINE configs[1]: "random-policy actions, env step +
+// reward only"): nsteps x (action draw, step) queued back to back on `stream`.  At 4 096 small environments a step
+// kernel lasts a few microseconds, less than one interpreter-level call, so the loop has to live below the FFI.
+extern "C" int uavsim_run_random_policy(uavsim_t *h, int mode, double coop, uint64_t seed, int64_t first_step,
+                                        int64_t nsteps, void *stream) {
+  int rc = check_step_args(h, mode, coop, "uavsim_run_random_policy");
+  if (rc) return rc;
+  if (nsteps < 0) { SET_ERR("uavsim_run_random_policy: nsteps < 0"); return UAVSIM_ERR_ARG; }
+  for (int64_t k = 0; k < nsteps; k++) {
+    rc = uavsim_random_actions(h, seed, first_step + k, stream);
+    if (rc) return rc;
+    rc = uavsim_step(h, mode, coop, stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 extern "C" int uavsim_step_host(uavsim_t *h, int mode, double coop, const int32_t *h_actions, float *h_obs,
                                 float *h_rew4, int32_t *h_covered, int chunks, void *stream) {
   int rc = check_step_args(h, mode, coop, "uavsim_step_host");

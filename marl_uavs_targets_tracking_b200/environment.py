@@ -245,6 +245,19 @@ class BatchedEnvironment:
             _cabi.check(self._lib.uavsim_step(self._h, mode, coop, self._stream()), "uavsim_step")
         return self._obs, self._rew4, self._covered
 
+    def run_random_policy(self, config, pmi, seed, first_step, nsteps):
+        """`nsteps` random-policy steps queued from C without returning to Python in between
+        (uavsim_run_random_policy): actions of step k are Philox(seed; agent, env, first_step + k), exactly what
+        `random_actions(seed, first_step + k)` followed by `step_device` gives.  Returns the last step's outputs."""
+        if self._h is None:
+            raise UavSimError("step before reset")
+        self._sync_weights(config)
+        mode, coop = self._mode(config, pmi)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.uavsim_run_random_policy(self._h, mode, coop, C.c_uint64(seed), int(first_step),
+                                                           int(nsteps), self._stream()), "uavsim_run_random_policy")
+        return self._obs, self._rew4, self._covered
+
     def step_host(self, config, pmi, h_actions, h_obs=None, h_rew4=None, h_covered=None, chunks=4):
         """uavsim_step_host: host (ideally pinned) int32 actions [E,n] in, host obs/rew4/covered out."""
         if self._h is None:

@@ -350,6 +350,25 @@ def test_reference_shaped_api_single_env():
     env.close()
 
 
+def test_device_side_rollout_loop_equals_stepwise_calls():
+    """uavsim_run_random_policy (loop below the FFI) == random_actions + step per step, bit for bit, statistics included."""
+    from marl_uavs_targets_tracking_b200 import default_config
+    cfg = default_config("MAAC-G", 10, 10)
+    a, b = _env(10, 10, cfg, 500, seed=9), _env(10, 10, cfg, 500, seed=9)
+    a.reset(cfg)
+    b.reset(cfg)
+    for t in range(37):
+        a.random_actions(11, t)
+        oa, ra, ca = a.step_device(cfg, None)
+    ob, rb, cb = b.run_random_policy(cfg, None, 11, 0, 37)
+    assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(ca, cb)
+    sa, sb = a.get_state(), b.get_state()
+    assert all(torch.equal(sa[k], sb[k]) for k in sa)
+    assert a.episode_stats() == b.episode_stats()
+    a.close()
+    b.close()
+
+
 def test_trace_files_have_the_reference_layout(tmp_path):
     """Row f-4: `save_position` / `save_covered_num` write what src/environment.py:229-244 writes -- u_xy<k>.csv is the
     (n_uav, steps, 2) array flattened to rows (UAV-major), header `x,y`; covered_target_num<k>.csv one count per step.
