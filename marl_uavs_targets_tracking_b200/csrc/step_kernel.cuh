@@ -252,29 +252,32 @@ __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
 }
 __device__ __forceinline__ uint32_t prefilter(const float4 *__restrict__ pf, int len, float xf, float yf, float thr) {
   constexpr int U = UAVSIM_PF_UNROLL;
-  const uint64_t xf2 = pack2(xf, xf), yf2 = pack2(yf, yf);
+  const uint64_t xf2 = pack2(xf, xf), yf2 = pack2(yf, yf), nthr2 = pack2(-thr, -thr);
+  // t = dx*dx + (dy*dy - thr) as two packed FMAs: negative exactly when the pair is a candidate (the two roundings,
+  // <= 2 ulp of thr, are inside the 3 ulp the guard of prefilter_threshold() reserves for the arithmetic, and the
+  // guard is doubled on top).  The sign bit is shifted into the mask with one funnel shift per partner -- no compare,
+  // no select; the first partner ends up in the highest bit, undone by one bit reversal per chunk.
   uint32_t mask = 0;
-  auto pair_bits = [&](int k) -> uint32_t {  // partners 2k, 2k+1 of the chunk -> two bits
-    const float4 p = pf[k];
-    uint64_t dx, dy, d2;
-    asm("sub.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(pack2(p.x, p.y)), "l"(xf2));
-    asm("sub.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(pack2(p.z, p.w)), "l"(yf2));
-    asm("mul.f32x2 %0, %1, %1;" : "=l"(d2) : "l"(dy));
-    asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(d2) : "l"(dx), "l"(d2));
-    const float d2a = __uint_as_float((uint32_t)d2), d2b = __uint_as_float((uint32_t)(d2 >> 32));
-    return ((d2a <= thr) ? 1u : 0u) | ((d2b <= thr) ? 2u : 0u);
+  auto pair_bits = [&](int k) {  // partners 2k, 2k+1 of the chunk
+    const ulonglong2 p = reinterpret_cast<const ulonglong2 *>(pf)[k];  // {x0, x1}, {y0, y1}: one 128-bit load
+    uint64_t dx, dy, t;
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(p.x), "l"(xf2));
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(p.y), "l"(yf2));
+    asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(t) : "l"(dy), "l"(nthr2));
+    asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(t) : "l"(dx), "l"(t));
+    mask = __funnelshift_l((uint32_t)t, mask, 1);
+    mask = __funnelshift_l((uint32_t)(t >> 32), mask, 1);
   };
   int jj = 0;
 #pragma unroll 1
   for (; jj + U <= len; jj += U) {
-    uint32_t b = 0;
 #pragma unroll
-    for (int u = 0; u < U / 2; u++) b |= pair_bits(jj / 2 + u) << (2 * u);
-    mask |= b << jj;
+    for (int u = 0; u < U / 2; u++) pair_bits(jj / 2 + u);
   }
 #pragma unroll 1
-  for (; jj < len; jj += 2) mask |= pair_bits(jj / 2) << jj;
-  return mask & low_bits(len);
+  for (; jj < len; jj += 2) pair_bits(jj / 2);
+  // jj partners went through (len rounded up to even; the odd trailing slot holds +huge: t = +inf, bit 0)
+  return jj ? (__brev(mask) >> (32 - jj)) & low_bits(len) : 0u;
 }
 
 // One chunk of up to 32 partner UAVs j = jb .. jb+len-1 for UAV i.  Partners with j < i moved before i: their
