@@ -132,6 +132,22 @@ __device__ __forceinline__ double wrap_heading(double h) {
   return x - PI_D;
 }
 
+// Hot-loop loads through an explicit 32-bit shared address.  With C++ pointers the compiler re-derives the base of the
+// dynamic shared array (S2UR SR_CgaCtaId + UMOV + ULEA + IMAD.U32) next to almost every access instead of keeping it
+// in a register -- ~5 % of the issued instructions, twice per trip of the candidate loops; an address that went through
+// an opaque asm once has to stay in its register.
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t v) { asm volatile("mov.b32 %0, %0;" : "+r"(v)); return v; }
+__device__ __forceinline__ double2 lds_d2(uint32_t a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int lds_i32(uint32_t a) {
+  int v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+
 // what phase 1 produces for one UAV
 struct AgentOut {
   double tt, dup;         // raw tracking reward / duplicate punishment (before normalisation)
@@ -288,7 +304,7 @@ __device__ __forceinline__ uint32_t prefilter(const float4 *__restrict__ pf, int
 // the new one, so co is prefiltered on the NEW position with the threshold dc + dt*v.
 // One generic routine for every chunk (kept small on purpose).  Returns the neighbour bits (d <= dp).
 template <bool MASKS>
-__device__ __forceinline__ uint32_t pair_chunk(const KParams &P, const UavSimBuffers &B, const EnvView V, int jb, int len,
+__device__ __forceinline__ uint32_t pair_chunk(const KParams &P, const UavSimBuffers &B, const EnvView V, uint32_t sb, int jb, int len,
                                                int i, double xi, double yi, float xf, float yf, bool far_env,
                                                float k_ex0, float k_ex1, CommAcc &A, double &dup, int64_t mrow_u) {
   const int sj = i - jb;                                   // bits below sj moved before i, bits above move after
@@ -310,15 +326,15 @@ __device__ __forceinline__ uint32_t pair_chunk(const KParams &P, const UavSimBuf
   // (B) exact fp64 evaluation of the candidates only.  Each lane walks its own bits (ascending j, like the
   // reference's loops); the warp runs max-over-lanes trips, so the two lists get two lean loops instead of one
   // fat one.  Sums over the two lists commute up to fp64 rounding of the (order-dependent) additions.
-  const double2 *npos = V.npos(), *nhd = V.nhd(), *opos = V.opos(), *ohd = V.ohd();
-  const int *na_ = V.na_(), *oa = V.oa();
+  const uint32_t a_npos = sb + V.L.npos, a_nhd = sb + V.L.nhd, a_opos = sb + V.L.opos, a_ohd = sb + V.L.ohd;
+  const uint32_t a_na = sb + V.L.na_, a_oa = sb + V.L.oa;
   uint32_t nbits = 0;
 #pragma unroll 1
   while (cn) {  // partner's NEW position: duplicate term, neighbour bit, and communication if it moved first
     const int jj = __ffs((int)cn) - 1;
     cn &= cn - 1;
     const int j = jb + jj;
-    const double2 np = npos[j];
+    const double2 np = lds_d2(a_npos + 16u * (uint32_t)j);
     const double dxn = np.x - xi, dyn = np.y - yi;
     const double d2n = dxn * dxn + dyn * dyn;
     const bool hd = d2n <= P.s_2dp_le;  // uav.py:225
@@ -327,8 +343,8 @@ __device__ __forceinline__ uint32_t pair_chunk(const KParams &P, const UavSimBuf
     if (hd) dup += (double)fast_ex2f(fmaf(fast_sqrtf((float)d2n), k_ex1, k_ex0));  // exp((2dp - d)/(2dp))
     if (hn) nbits |= 1u << jj;
     if (hc) {
-      const double2 h = nhd[j];
-      A.sx += dxn; A.sy += dyn; A.sc += h.x; A.ss += h.y; A.sa += na_[j]; A.cnt++;
+      const double2 h = lds_d2(a_nhd + 16u * (uint32_t)j);
+      A.sx += dxn; A.sy += dyn; A.sc += h.x; A.ss += h.y; A.sa += lds_i32(a_na + 4u * (uint32_t)j); A.cnt++;
     }
     if (MASKS) { B.nbr_mask[mrow_u + j] = hn; B.dup_mask[mrow_u + j] = hd; if (hc) B.comm_mask[mrow_u + j] = 1; }
   }
@@ -337,12 +353,12 @@ __device__ __forceinline__ uint32_t pair_chunk(const KParams &P, const UavSimBuf
     const int jj = __ffs((int)co) - 1;
     co &= co - 1;
     const int j = jb + jj;
-    const double2 op = opos[j];
+    const double2 op = lds_d2(a_opos + 16u * (uint32_t)j);
     const double dxo = op.x - xi, dyo = op.y - yi;
     const double d2o = dxo * dxo + dyo * dyo;
     if (d2o <= P.s_dc_le) {
-      const double2 h = ohd[j];
-      A.sx += dxo; A.sy += dyo; A.sc += h.x; A.ss += h.y; A.sa += oa[j]; A.cnt++;
+      const double2 h = lds_d2(a_ohd + 16u * (uint32_t)j);
+      A.sx += dxo; A.sy += dyo; A.sc += h.x; A.ss += h.y; A.sa += lds_i32(a_oa + 4u * (uint32_t)j); A.cnt++;
       if (MASKS) B.comm_mask[mrow_u + j] = 1;
     }
   }
@@ -350,7 +366,7 @@ __device__ __forceinline__ uint32_t pair_chunk(const KParams &P, const UavSimBuf
 }
 
 template <int CN, int CM, bool WARP_ENV, bool MASKS>
-__device__ __forceinline__ void agent_fast(const KParams &P, const UavSimBuffers &B, const EnvView V, int *tcnt, int i,
+__device__ __forceinline__ void agent_fast(const KParams &P, const UavSimBuffers &B, const EnvView V, uint32_t sb, int *tcnt, int i,
                                            int n_rt, int m_rt, bool far_env, float *ob, int64_t mrow_t, int64_t mrow_u,
                                            AgentOut &O) {
   const int n = CN ? CN : n_rt, m = CM ? CM : m_rt;
@@ -364,7 +380,7 @@ __device__ __forceinline__ void agent_fast(const KParams &P, const UavSimBuffers
     const float inv_dp_f = (float)(1.0 / P.dp);
     double ox = 0, oy = 0, ovx = 0, ovy = 0, tt = 0;
     int nobs = 0;
-    const double2 *tpos = V.tpos(), *tvel = V.tvel();
+    const uint32_t a_tpos = sb + V.L.tpos, a_tvel = sb + V.L.tvel;
 #pragma unroll 1
     for (int tb = 0; tb < m; tb += 32) {
       const int len = min(32, m - tb);
@@ -377,13 +393,13 @@ __device__ __forceinline__ void agent_fast(const KParams &P, const UavSimBuffers
         const int jj = __ffs((int)ct) - 1;
         ct &= ct - 1;
         const int t = tb + jj;
-        const double2 tp = tpos[t];
+        const double2 tp = lds_d2(a_tpos + 16u * (uint32_t)t);
         const double dx = tp.x - xi, dy = tp.y - yi;
         const double d2 = dx * dx + dy * dy;
         const bool hit = d2 <= P.s_dp_le;
         if (MASKS) { B.obs_mask[mrow_t + t] = hit; B.cover_mask[mrow_t + t] = (d2 <= P.s_dp_lt); }
         if (hit) {
-          const double2 tv = tvel[t];
+          const double2 tv = lds_d2(a_tvel + 16u * (uint32_t)t);
           ox += dx; oy += dy; ovx += tv.x; ovy += tv.y;
           nobs++;
           tt += (double)(2.0f - fast_sqrtf((float)d2) * inv_dp_f);  // 1 + (dp - d)/dp
@@ -413,7 +429,7 @@ __device__ __forceinline__ void agent_fast(const KParams &P, const UavSimBuffers
   for (int c = 0; c < 4; c++) {
     const int jb = 32 * c;
     uint32_t nbits = 0;
-    if (jb < n) nbits = pair_chunk<MASKS>(P, B, V, jb, min(32, n - jb), i, xi, yi, xf, yf, far_env, k_ex0, k_ex1, A, dup, mrow_u);
+    if (jb < n) nbits = pair_chunk<MASKS>(P, B, V, sb, jb, min(32, n - jb), i, xi, yi, xf, yf, far_env, k_ex0, k_ex1, A, dup, mrow_u);
     O.nb[c] = nbits;
   }
 
@@ -450,6 +466,7 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
   const int tid = threadIdx.x;
   const CtaSmem S = carve(smem_raw, n, m, P.na, epb, L.stride);
   const int64_t plane = P.E * n;  // rew4 plane stride
+  const uint32_t s_env0 = opaque_u32((uint32_t)__cvta_generic_to_shared(S.env));
 
   for (int k = tid; k < 3 * P.na; k += NT) S.dth[k] = g_dth[k];
   for (int k = tid; k < epb; k += NT) {  // odd trailing slots of the paired fp32 arrays: never a candidate
@@ -542,7 +559,7 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
       // row weights differ from 1 only if |x| < 2 and |y| < 2 (|rx|,|ry| <= 1 for any row in range)
       const bool near_origin = fabs(xi) < 2.0 && fabs(yi) < 2.0;
       if (near_origin) agent_exact<MASKS>(P, B, V, S.tcnt + el * m, i, n, m, ob, mrow_t, mrow_u, &O);
-      else agent_fast<CN, CM, WARP_ENV, MASKS>(P, B, V, S.tcnt + el * m, i, n, m, S.far[el] != 0, ob, mrow_t, mrow_u, O);
+      else agent_fast<CN, CM, WARP_ENV, MASKS>(P, B, V, s_env0 + (uint32_t)el * (uint32_t)L.stride, S.tcnt + el * m, i, n, m, S.far[el] != 0, ob, mrow_t, mrow_u, O);
       if (MASKS) { B.comm_mask[mrow_u + i] = 0; B.nbr_mask[mrow_u + i] = 0; B.dup_mask[mrow_u + i] = 0; }
       ob[9] = (float)(xi * P.inv_dc);
       ob[10] = (float)(yi * P.inv_dc);
