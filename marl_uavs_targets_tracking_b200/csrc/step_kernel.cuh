@@ -332,16 +332,17 @@ __device__ __forceinline__ uint32_t pair_chunk(const KParams &P, const UavSimBuf
 #pragma unroll 1
   while (cn) {  // partner's NEW position: duplicate term, neighbour bit, and communication if it moved first
     const int jj = __ffs((int)cn) - 1;
-    cn &= cn - 1;
+    const uint32_t rest = cn & (cn - 1), bit = cn ^ rest;  // bit = 1 << jj without the shift
+    cn = rest;
     const int j = jb + jj;
     const double2 np = lds_d2(a_npos + 16u * (uint32_t)j);
     const double dxn = np.x - xi, dyn = np.y - yi;
     const double d2n = dxn * dxn + dyn * dyn;
     const bool hd = d2n <= P.s_2dp_le;  // uav.py:225
     const bool hn = d2n <= P.s_dp_le;   // uav.py:305
-    const bool hc = (jj < sj) && (d2n <= P.s_dc_le);  // uav.py:135, partner already at its new state
+    const bool hc = (bit & lt) && (d2n <= P.s_dc_le);  // uav.py:135, partner already at its new state (jj < sj)
     if (hd) dup += (double)fast_ex2f(fmaf(fast_sqrtf((float)d2n), k_ex1, k_ex0));  // exp((2dp - d)/(2dp))
-    if (hn) nbits |= 1u << jj;
+    if (hn) nbits |= bit;
     if (hc) {
       const double2 h = lds_d2(a_nhd + 16u * (uint32_t)j);
       A.sx += dxn; A.sy += dyn; A.sc += h.x; A.ss += h.y; A.sa += lds_i32(a_na + 4u * (uint32_t)j); A.cnt++;
