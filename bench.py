@@ -385,6 +385,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
+    # host buffers of the e2e leg next to this GPU's PCIe root (one process per GPU); undone before the CPU baseline
+    from marl_uavs_targets_tracking_b200 import bind_host_to_gpu
+    affinity = None if os.environ.get("UAVSIM_NO_BIND") else bind_host_to_gpu(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
@@ -433,6 +436,9 @@ def main():
                "episode_stats": main_res["episode_stats"], "other_workloads": extras}
         if main_res.get("trace"):
             out["ms_per_step_trace"] = {"every": args.trace_every, "ms": main_res["trace"]}
+        if affinity:
+            os.sched_setaffinity(0, affinity[0])
+        out["host_affinity"] = None if not affinity else {"cpus": len(affinity[1]), "of": len(affinity[0])}
         if world == 1 and not args.no_extras:
             v, sample, _, _, _ = cpu_oracle_rate(n, m, main_res["method"], args.cpu_seconds, os.cpu_count() or 1)
             out["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": os.cpu_count() or 1, "kind": "port",

@@ -5,7 +5,7 @@ C ABI in include/uavsim.h; no CPU path."""
 from ._cabi import MODE_MEAN, MODE_PMI, MODE_SELF, UavSimError  # noqa: F401
 from .environment import BatchedEnvironment, Environment, params_from_config  # noqa: F401
 from .pmi import PMINetwork, fold_pmi  # noqa: F401
-from .distributed import shard_envs, reduce_episode_stats, episode_summary  # noqa: F401
+from .distributed import shard_envs, reduce_episode_stats, episode_summary, bind_host_to_gpu  # noqa: F401
 from .config import default_config  # noqa: F401
 from .replay import PrioritizedReplayBuffer  # noqa: F401
 

@@ -5,6 +5,8 @@ Environments are independent, so rank r of R owns the contiguous global ids
 <= 8 doubles per episode (the sums src/train.py:181-192 accumulates): NCCL over NVLink on GPUs,
 gloo in the CPU tests.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -43,3 +45,29 @@ def episode_summary(stats, n_uav):
             "duplicate_tracking_punishment_return": stats["duplicate_tracking_punishment"] / agent_steps,
             "average_covered_targets": stats["covered_sum"] / max(stats["env_steps"], 1.0),
             "max_covered_targets": stats["covered_max"]}
+
+
+def bind_host_to_gpu(device_index):
+    """Pin this process to the CPUs NVML reports as local to the GPU (same NUMA node / PCIe root), so pinned host
+    buffers allocated afterwards are first-touched next to the link they are copied over.  With one process per GPU
+    and host-buffer steps (`uavsim_step_host`) every rank otherwise stages through whichever node the scheduler
+    picked.  Returns (previous affinity, new affinity) or None when NVML / the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+        try:
+            handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + uuid)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        before = os.sched_getaffinity(0)
+        cpus &= before
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return before, cpus
+    except Exception:
+        return None
