@@ -6,40 +6,47 @@
 //
 // Mapping.  One CTA per SM, persistent over groups of environments, warp-specialised:
 //   warp 0 (one elected lane)  issues every tcgen05.mma (kind::tf32, M = 128, N = 128, K = 8) and the commits.
-//   warp 17 (one elected lane) streams the fc1 weight chunks into the ring (cp.async.bulk, TMA engine).
-//   warps 1..16 (512 threads)  one thread per pair row of a SET of four 128-row tiles (warp w: tile (w-1)/4, TMEM lane
-//                              quarter w%4): they build the row, run layer 0 on the CUDA cores, write the A operand,
-//                              and later do the epilogue.
-// The two sides meet only through mbarriers (A-ready / B-full / stage-free / accumulators-full / accumulators-free);
-// there is no CTA-wide barrier inside a set.
-// The 384 -> 128 layer is a [128 x 384] x [384 x 128] GEMM per tile, fp32 accumulators in tensor memory.  The four
-// tiles of a set own the four 128-column quarters of the SM's 512 TMEM columns and share every fc1 chunk: the fc1
-// matrix (393 KB split) does not fit in shared memory and streaming it from L2 once per TILE was the measured floor of
-// the previous version (44 GB/s per SM, 6.5 TB/s over the chip); once per SET is a quarter of that.
+//   warp 17 (one elected lane) streams the fc1 weight chunks into a shared-memory ring (cp.async.bulk, TMA engine).
+//   warps 1..16 (512 threads)  two threads per pair row of a SET of two 128-row tiles (warp w: tile ((w-1)/4)%2, TMEM
+//                              lane quarter w%4, unit half (w-1)/8): they build the row, run layer 0 on the CUDA
+//                              cores, write the A operand, and later do the epilogue.
+// The roles meet only through mbarriers (A-ready / B-full / stage-free / accumulators-full / accumulators-free) over
+// 4-stage rings with a static schedule; there is no CTA-wide barrier inside a set.
+// The 384 -> 128 layer is a [128 x 384] x [384 x 128] GEMM per tile, fp32 accumulators in tensor memory.
+// Tensor memory map (512 columns): accumulators of the two tiles in columns 0..255; the A operand lives in TENSOR
+// MEMORY too (tcgen05.mma with A from TMEM), columns 256..511 = 4 stages x 2 tiles x {hi k0-7, hi k8-15, lo k0-7,
+// lo k8-15}: the producers write their layer-0 activations with tcgen05.st straight from registers.  With A in shared
+// memory the three MMAs of a K-slice read 24 KB of operands (A 4 KB + B 4 KB each) and the producers store another
+// 8 KB: the shared-memory pipe, not the tensor pipe, was the limit (66 % busy at 57 % tensor activity); now only the
+// B operand (12 KB per slice) comes from shared memory.
 // Precision: single-pass TF32 (10-bit mantissa) misses the 1e-5 bar, so both operands are split
 // x = hi + lo (hi = tf32(x), lo = tf32(x - hi)) and every K-slice runs three MMAs hi*hi + lo*hi + hi*lo -- fp32-class
 // products, fp32 accumulation.
-//   A (activations after layer 0): computed per 8-unit K-chunk into a 4-stage ring (block-diagonal 12 -> 384, <= 5 FMAs per unit),
-//     split, and written straight into the canonical K-major no-swizzle UMMA layout
-//     byte(r, k) = (k/4)*2048 + (r/8)*128 + (r%8)*16 + (k%4)*4   (8x16-byte core matrices, LBO 2048, SBO 128)
-//     -- a thread writes one 16-byte vector per 4 units, consecutive threads consecutive vectors (no bank conflicts).
-//   B (fc1 weights): pre-split and pre-arranged on the host in the same layout, one 8 KB block (hi | lo) per
-//     8-unit chunk = one bulk copy, mbarrier complete_tx.
-// Epilogue: tcgen05.ld (32 lanes x 32 columns per warp and instruction) -> bias + ReLU -> dot with fc2 in the row's
-// thread -> logit in shared memory; then softmax + mix per UAV.
+//   A (activations after layer 0): block-diagonal 12 -> 384, <= 5 FMAs per unit, two units per packed FFMA2; row r of a
+//     tile is TMEM lane r, one 32-bit column per K element.
+//   B (fc1 weights): pre-split and pre-arranged on the host in the canonical K-major no-swizzle UMMA layout
+//     byte(o, k) = (k/4)*2048 + (o/8)*128 + (o%8)*16 + (k%4)*4   (8x16-byte core matrices, LBO 2048, SBO 128),
+//     one 16 KB block (hi | lo) per 16-unit chunk = one bulk copy, mbarrier complete_tx.
+// Epilogue: tcgen05.ld (32 lanes x 32 columns per warp and instruction) -> bias + ReLU -> dot with fc2, the two
+// threads of a row take 64 columns each -> logit in shared memory; then softmax + mix per UAV.
 #pragma once
 #include "common.cuh"
 
-#define TC_SET 4             // tiles per set = accumulators in tensor memory (4 x 128 columns)
-#define TC_NP (128 * TC_SET) // producer / epilogue threads (warps 1 .. 16)
+#ifndef TC_WAIT_HINT
+#define TC_WAIT_HINT 20000u
+#endif
+#define TC_SET 2             // tiles per set = accumulators in tensor memory (2 x 128 columns)
+#define TC_NP 512            // producer / epilogue threads (warps 1 .. 16), two per pair row
 #define TC_NT (TC_NP + 64)   // + warp 0 = MMA issue, warp 17 = fc1 chunk loader (TMA)
 #define TC_H 128
 #define TC_H3 384
-#define TC_KC 8              // hidden units per K-chunk = one MMA K-slice
-#define TC_NS 4              // stages of the operand ring
+#define TC_KC 16             // hidden units per ring stage = two MMA K-slices
+#define TC_NS 4              // stages of the operand rings
 #define TC_NCHUNK (TC_H3 / TC_KC)
-#define TC_A_BYTES 4096      // one 128 x 8 fp32 operand block (hi or lo)
-#define TC_STAGE_BYTES ((2 * TC_SET + 2) * TC_A_BYTES)  // 4 x (A_hi, A_lo) + B_hi + B_lo = 40 KB
+#define TC_A_BYTES 8192      // one 128 x 16 fp32 weight block (hi or lo)
+#define TC_STAGE_BYTES (2 * TC_A_BYTES)  // B_hi + B_lo = 16 KB
+#define TC_ACOL0 256u        // first TMEM column of the A ring
+#define TC_ACOLS 64u         // TMEM columns per A stage: 2 tiles x (16 hi + 16 lo)
 #define TC_AMAX 256          // UAVs per environment group
 #define TC_PMAX 8192         // neighbour pairs per environment group
 
@@ -47,14 +54,15 @@
 #define TC_IDESC ((1u << 4) | (2u << 7) | (2u << 10) | ((TC_H >> 3) << 17) | ((128u >> 4) << 24))
 
 struct TcSmem {  // byte offsets inside dynamic shared memory (base is 1024-byte aligned)
-  static constexpr uint32_t stage = 0;                                   // TC_NS x TC_STAGE_BYTES
+  static constexpr uint32_t stage = 0;                                   // TC_NS x TC_STAGE_BYTES (fc1 chunks only)
   static constexpr uint32_t obs = TC_NS * TC_STAGE_BYTES;                   // float [AMAX*12]
   static constexpr uint32_t raw = obs + TC_AMAX * 12 * 4;                // double [AMAX]
   static constexpr uint32_t nbr = raw + TC_AMAX * 8;                     // uint64 [AMAX*2]
   static constexpr uint32_t off = nbr + TC_AMAX * 16;                    // uint32 [AMAX+4]
   static constexpr uint32_t logit = off + (TC_AMAX + 4) * 4;             // float [PMAX]
   static constexpr uint32_t w0 = logit + TC_PMAX * 4;                    // float [192*12]: per unit pair, bias and 5 weights interleaved
-  static constexpr uint32_t b1 = w0 + (TC_H3 / 2) * 12 * 4;                    // float [128]
+  static constexpr uint32_t part = w0 + (TC_H3 / 2) * 12 * 4;          // float [2][128] fc2 partial dots of the second thread of a row
+  static constexpr uint32_t b1 = part + TC_SET * 128 * 4;                    // float [128]
   static constexpr uint32_t w2 = b1 + TC_H * 4;                          // float [128]
   static constexpr uint32_t red = w2 + TC_H * 4;                         // double [7 per warp]
   static constexpr uint32_t bar = red + (TC_NT / 32) * 7 * 8;            // 3 x TC_NS + 2 mbarriers + tmem pointer
@@ -81,10 +89,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   for (uint32_t spin = 0; !done; spin++) {
     asm volatile(
         "{\n\t.reg .pred P1;\n\t"
+#ifdef TC_WAIT_NOHINT
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+#endif
         "selp.b32 %0, 1, 0, P1;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity), "r"(20000u)
+        : "r"(bar), "r"(parity), "r"(TC_WAIT_HINT)
         : "memory");
     if (spin > (1u << 22)) __trap();
   }
@@ -129,6 +141,23 @@ __device__ __forceinline__ void umma_tf32_p(uint32_t lead, uint32_t tmem_d, uint
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(TC_IDESC), "r"(accumulate), "r"(lead)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand read from tensor memory (lane = row, one column per tf32 element)
+__device__ __forceinline__ void umma_tf32_ts_p(uint32_t lead, uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(TC_IDESC), "r"(accumulate), "r"(lead)
+      : "memory");
+}
+// registers -> tensor memory: lane l of the warp writes its 8 values to TMEM lane (quarter base + l), columns c .. c+7
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float *v) {
+  const uint32_t *u = reinterpret_cast<const uint32_t *>(v);
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
+               : "memory");
+}
 __device__ __forceinline__ void umma_commit_p(uint32_t lead, uint32_t bar) {
   asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
                "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(lead) : "memory");
@@ -168,7 +197,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
 
 struct PmiTcDev {
   const float *w0, *b0, *b1, *w2;  // [384*5] [384] [128] [128] folded fp32
-  const float *w1_tiles;           // [48][2][128 x 8] fc1 pre-split (hi | lo) in the UMMA layout
+  const float *w1_tiles;           // [24][2][128 x 16] fc1 pre-split (hi | lo) in the UMMA layout
   float b2;
 };
 
@@ -179,13 +208,14 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
   const int n = P.n, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool producer = warp >= 1 && warp <= TC_NP / 32;   // warp 0 = MMA issue, last warp = weight loader
   // producers: hardware warp w may only touch TMEM lanes 32*(w%4)..+31, so rows follow the warp id
-  const int row = 32 * (warp & 3) + lane, mytile = (warp - 1) >> 2, pt = tid - 32;
+  const int row = 32 * (warp & 3) + lane, mytile = ((warp - 1) >> 2) & 1, half = (warp - 1) >> 3, pt = tid - 32;
   float *s_obs = reinterpret_cast<float *>(smem + TcSmem::obs);
   double *s_raw = reinterpret_cast<double *>(smem + TcSmem::raw);
   uint64_t *s_nbr = reinterpret_cast<uint64_t *>(smem + TcSmem::nbr);
   uint32_t *s_off = reinterpret_cast<uint32_t *>(smem + TcSmem::off);
   float *s_logit = reinterpret_cast<float *>(smem + TcSmem::logit);
   float *s_w0 = reinterpret_cast<float *>(smem + TcSmem::w0);
+  float *s_part = reinterpret_cast<float *>(smem + TcSmem::part);
   float *s_b1 = reinterpret_cast<float *>(smem + TcSmem::b1);
   float *s_w2 = reinterpret_cast<float *>(smem + TcSmem::w2);
   double *s_red = reinterpret_cast<double *>(smem + TcSmem::red);
@@ -193,7 +223,7 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + TcSmem::bar;
   const uint32_t bar_bfull = bar0, bar_aready = bar0 + 8 * TC_NS, bar_free = bar0 + 16 * TC_NS;  // [TC_NS]: one per stage
-  const uint32_t bar_accfull = bar0 + 24 * TC_NS, bar_accfree = bar_accfull + 8;               // one each: the set's accumulators
+  const uint32_t bar_accfull = bar0 + 24 * TC_NS, bar_accfree = bar_accfull + 8;
 
   for (int k = tid; k < (TC_H3 / 2) * 12; k += TC_NT) {  // unit pair j: {b, b', w0, w0', .. w4, w4'} -> three 128-bit loads
     const int u = 2 * (k / 12) + (k & 1), e = (k % 12) >> 1;
@@ -202,7 +232,7 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
   for (int k = tid; k < TC_H; k += TC_NT) { s_b1[k] = W.b1[k]; s_w2[k] = W.w2[k]; }
   if (tid == 0) {
     for (int k = 0; k < TC_NS; k++) {
-      mbar_init(bar_bfull + 8 * k, 1);              // expect_tx by the control lane + TMA bytes
+      mbar_init(bar_bfull + 8 * k, 1);              // expect_tx by the loader lane + TMA bytes
       mbar_init(bar_aready + 8 * k, TC_NP / 32);    // one arrive per producer warp
       mbar_init(bar_free + 8 * k, 1);               // tcgen05.commit
     }
@@ -210,7 +240,7 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
     mbar_init(bar_accfree, TC_NP / 32);             // one arrive per producer warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {  // all of tensor memory: four 128-column fp32 accumulators, allocated by one warp
+  if (warp == 0) {  // all of tensor memory: two 128-column fp32 accumulators + the A ring, allocated by one warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -219,9 +249,9 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *s_tmem;
 
-  // Static ring schedule: a set is TC_NCHUNK = 48 chunks and the ring has TC_NS = 4 stages, so chunk c of every set
-  // uses stage c % 4 and it is that stage's (12 * set + c / 4)-th use: the mbarrier phase parity is (c / 4) & 1 in
-  // every set, and all shared-memory addresses and descriptors are compile-time offsets from the base.
+  // Static ring schedule: a set is TC_NCHUNK = 24 chunks and the rings have TC_NS = 4 stages, so chunk c of every set
+  // uses stage c % 4 and it is that stage's (6 * set + c / 4)-th use: the mbarrier phase parity is (c / 4) & 1 in
+  // every set, and all shared-memory / tensor-memory addresses are compile-time offsets from the bases.
   static_assert(TC_NCHUNK % (2 * TC_NS) == 0, "ring schedule assumes an even number of ring turns per set");
   uint32_t t = 0;   // sets processed so far by this CTA (phase of the accumulator barriers); same sequence in all roles
   const int64_t ngroups = (env_count + G - 1) / G;
@@ -268,27 +298,28 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
           const uint32_t par = c4 & 1;
 #pragma unroll
           for (int s = 0; s < TC_NS; s++) {
-            const uint32_t stage = sbase + TcSmem::stage + s * TC_STAGE_BYTES;
-            mbar_wait(bar_aready + 8 * s, par);  // producers have written A
-            mbar_wait(bar_bfull + 8 * s, par);   // weights have landed
+            mbar_wait(bar_aready + 8 * s, par);  // producers have written A (tensor memory)
+            mbar_wait(bar_bfull + 8 * s, par);   // weights have landed (shared memory)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // descriptors differ only in the 14-bit address field: add (byte offset >> 4) to the low word
-            const uint64_t dbh = umma_desc(stage + 2 * TC_SET * TC_A_BYTES), dbl = dbh + (TC_A_BYTES >> 4);
-            const uint64_t da0 = umma_desc(stage);
-            const uint32_t acc = (c4 | s) ? 1u : 0u;
+            // B descriptors differ only in the 14-bit address field: add (byte offset >> 4) to the low word
+            const uint64_t dbh0 = umma_desc(sbase + TcSmem::stage + s * TC_STAGE_BYTES), dbl0 = dbh0 + (TC_A_BYTES >> 4);
 #pragma unroll
             for (int q = 0; q < TC_SET; q++) {
               if (q < nts) {
-                const uint64_t dah = da0 + (uint64_t)(q * 2 * (TC_A_BYTES >> 4)), dal = dah + (TC_A_BYTES >> 4);
                 const uint32_t d_tmem = u_tmem + 128u * (uint32_t)q;
-                umma_tf32_p(lead, d_tmem, dah, dbh, acc);
+#pragma unroll
+                for (int ks = 0; ks < TC_KC / 8; ks++) {  // one MMA consumes K = 8: 8 TMEM columns of A, two core-matrix columns of B
+                  const uint32_t a_hi = u_tmem + TC_ACOL0 + TC_ACOLS * (uint32_t)s + 32u * (uint32_t)q + 8u * (uint32_t)ks, a_lo = a_hi + 16u;
+                  const uint64_t dbh = dbh0 + (uint64_t)(ks * 2 * (2048 >> 4)), dbl = dbl0 + (uint64_t)(ks * 2 * (2048 >> 4));
+                  umma_tf32_ts_p(lead, d_tmem, a_hi, dbh, (c4 | s | ks) ? 1u : 0u);
 #ifndef TC_ABL_MMA1
-                umma_tf32_p(lead, d_tmem, dal, dbh, 1u);
-                umma_tf32_p(lead, d_tmem, dah, dbl, 1u);
+                  umma_tf32_ts_p(lead, d_tmem, a_lo, dbh, 1u);
+                  umma_tf32_ts_p(lead, d_tmem, a_hi, dbl, 1u);
 #endif
+                }
               }
             }
-            umma_commit_p(lead, bar_free + 8 * s);  // stage reusable when these MMAs are done
+            umma_commit_p(lead, bar_free + 8 * s);  // both rings' stage s reusable when these MMAs are done
           }
         }
         umma_commit_p(lead, bar_accfull);  // accumulators complete
@@ -303,7 +334,7 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
 #pragma unroll
           for (int s = 0; s < TC_NS; s++) {
             if (t > 0 || c4 > 0) mbar_wait(bar_free + 8 * s, (c4 & 1) ^ 1);  // the MMAs of the previous use are done
-            load_chunk_p(lead, sbase + TcSmem::stage + s * TC_STAGE_BYTES + 2 * TC_SET * TC_A_BYTES,
+            load_chunk_p(lead, sbase + TcSmem::stage + s * TC_STAGE_BYTES,
                          W.w1_tiles + (size_t)(c4 * TC_NS + s) * (2 * TC_A_BYTES / 4), 2 * TC_A_BYTES, bar_bfull + 8 * s);
           }
         }
@@ -311,7 +342,7 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
     } else {
       // =============================== producers: rows, layer 0, epilogue ===============================
       for (int set = 0; set < nsets; set++, t++) {
-        const int p = (set * TC_SET + mytile) * 128 + row;   // this thread's pair row
+        const int p = (set * TC_SET + mytile) * 128 + row;   // this thread's pair row (shared with its partner warp)
         const bool live = set * TC_SET + mytile < ntiles;    // warp-uniform: the tile exists
         // ---- flat pair index -> (UAV a, its k-th neighbour b), x = la_a * la_b (uav.py:280-281)
         float x[12];
@@ -337,73 +368,75 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
 #pragma unroll
         for (int q = 0; q < 12; q++) xx[q] = tc_pack2(x[q], x[q]);
 
-        // ---- layer 0 per K-chunk of 8 hidden units into the stage ring.  The three input branches
+        // ---- layer 0 per ring stage of 16 hidden units; this thread computes the 8 units of K-slice `half` of its
+        //      row and writes them (hi and lo) into the stage's tensor-memory columns.  The three input branches
         //      (communication 5, observation 4, boundary/state 3 inputs; PMINet.py:45-58, BN folded) are unrolled
-        //      so the row stays in registers; each branch covers 16 chunks.
+        //      so the row stays in registers; each branch covers 8 chunks.
+        const uint32_t a_lane = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + TC_ACOL0 + 32u * (uint32_t)mytile + 8u * (uint32_t)half;
         auto run_chunk = [&](const int c, const uint64_t *xin, const int dim) {
           const uint32_t s = c % TC_NS, c4 = c / TC_NS;
           if (t > 0 || c4 > 0) {  // MMAs that read this stage have completed
             mbar_wait(bar_free + 8 * s, (c4 & 1) ^ 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           }
-          unsigned char *a_hi = smem + TcSmem::stage + (size_t)s * TC_STAGE_BYTES + (size_t)mytile * 2 * TC_A_BYTES;
-          unsigned char *a_lo = a_hi + TC_A_BYTES;
 #ifdef TC_ABL_NOPROD
           if (c < 0)
 #endif
           if (live) {
+            float hv[8], lv[8];
 #pragma unroll
-            for (int gq = 0; gq < TC_KC / 4; gq++) {
-              float hv[4], lv[4];
-#pragma unroll
-              for (int e = 0; e < 4; e += 2) {  // two units per packed fp32 instruction (FFMA2)
-                const float4 *wp = reinterpret_cast<const float4 *>(s_w0 + ((c * TC_KC + gq * 4 + e) >> 1) * 12);
-                const float4 q0 = wp[0], q1 = wp[1];  // b b' w0 w0' | w1 w1' w2 w2'
-                uint64_t acc = tc_pack2(q0.x, q0.y);
-                acc = tc_fma2(tc_pack2(q0.z, q0.w), xin[0], acc);
-                acc = tc_fma2(tc_pack2(q1.x, q1.y), xin[1], acc);
-                acc = tc_fma2(tc_pack2(q1.z, q1.w), xin[2], acc);
-                if (dim > 3) {
-                  const float4 q2 = wp[2];            // w3 w3' | w4 w4'
-                  acc = tc_fma2(tc_pack2(q2.x, q2.y), xin[3], acc);
-                  if (dim > 4) acc = tc_fma2(tc_pack2(q2.z, q2.w), xin[4], acc);
-                }
-                const float a0 = fmaxf(__uint_as_float((uint32_t)acc), 0.f), a1 = fmaxf(__uint_as_float((uint32_t)(acc >> 32)), 0.f);
-                hv[e] = tf32_rna(a0); hv[e + 1] = tf32_rna(a1);
-                lv[e] = tf32_rna(a0 - hv[e]); lv[e + 1] = tf32_rna(a1 - hv[e + 1]);
+            for (int e = 0; e < 8; e += 2) {  // two units per packed fp32 instruction (FFMA2)
+              const float4 *wp = reinterpret_cast<const float4 *>(s_w0 + ((c * TC_KC + half * 8 + e) >> 1) * 12);
+              const float4 q0 = wp[0], q1 = wp[1];  // b b' w0 w0' | w1 w1' w2 w2'
+              uint64_t acc = tc_pack2(q0.x, q0.y);
+              acc = tc_fma2(tc_pack2(q0.z, q0.w), xin[0], acc);
+              acc = tc_fma2(tc_pack2(q1.x, q1.y), xin[1], acc);
+              acc = tc_fma2(tc_pack2(q1.z, q1.w), xin[2], acc);
+              if (dim > 3) {
+                const float4 q2 = wp[2];            // w3 w3' | w4 w4'
+                acc = tc_fma2(tc_pack2(q2.x, q2.y), xin[3], acc);
+                if (dim > 4) acc = tc_fma2(tc_pack2(q2.z, q2.w), xin[4], acc);
               }
-              *reinterpret_cast<float4 *>(a_hi + gq * 2048 + row * 16) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-              *reinterpret_cast<float4 *>(a_lo + gq * 2048 + row * 16) = make_float4(lv[0], lv[1], lv[2], lv[3]);
+              const float a0 = fmaxf(__uint_as_float((uint32_t)acc), 0.f), a1 = fmaxf(__uint_as_float((uint32_t)(acc >> 32)), 0.f);
+              hv[e] = tf32_rna(a0); hv[e + 1] = tf32_rna(a1);
+              lv[e] = tf32_rna(a0 - hv[e]); lv[e + 1] = tf32_rna(a1 - hv[e + 1]);
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+            tmem_st8(a_lane + TC_ACOLS * s, hv);
+            tmem_st8(a_lane + TC_ACOLS * s + 16u, lv);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           }
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_aready + 8 * s);
         };
 #pragma unroll 1
-        for (int cc = 0; cc < 16; cc++) run_chunk(cc, xx, 5);
+        for (int cc = 0; cc < 8; cc++) run_chunk(cc, xx, 5);
 #pragma unroll 1
-        for (int cc = 16; cc < 32; cc++) run_chunk(cc, xx + 5, 4);
+        for (int cc = 8; cc < 16; cc++) run_chunk(cc, xx + 5, 4);
 #pragma unroll 1
-        for (int cc = 32; cc < 48; cc++) run_chunk(cc, xx + 9, 3);
+        for (int cc = 16; cc < 24; cc++) run_chunk(cc, xx + 9, 3);
 
-        // ---- epilogue: bias + ReLU + fc2 (PMINet.py:59-62) over the row's 128 accumulator columns
+        // ---- epilogue: bias + ReLU + fc2 (PMINet.py:59-62); the two threads of a row take 64 accumulator columns each
         mbar_wait(bar_accfull, t & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float part = 0.f;
         if (live) {
-          float part = 0.f;
 #pragma unroll 1
-          for (int cb = 0; cb < 128; cb += 32) {
+          for (int cb = half * 64; cb < half * 64 + 64; cb += 32) {
             float v[32];
             tmem_ld32(tmem_d + 128u * (uint32_t)mytile + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)cb, v);
 #pragma unroll
             for (int k = 0; k < 32; k++) part = fmaf(s_w2[cb + k], fmaxf(v[k] + s_b1[cb + k], 0.f), part);
           }
-          if (p < npairs) s_logit[p] = part + W.b2;
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_accfree);  // this warp's rows have left tensor memory
+        // combine the two halves of each row (producer-only named barrier: warps 0 and 17 are elsewhere)
+        if (half) s_part[mytile * 128 + row] = part;
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_NP) : "memory");
+        if (!half && p < npairs) s_logit[p] = (part + s_part[mytile * 128 + row]) + W.b2;
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_NP) : "memory");
       }
     }
     __syncthreads();
