@@ -6,10 +6,12 @@
 //
 // Mapping.  One CTA per SM, persistent over groups of environments, warp-specialised:
 //   warp 0 (one elected lane)  issues every tcgen05.mma (kind::tf32, M = 128, N = 128, K = 8) and the commits.
-//   warp 17 (one elected lane) streams the fc1 weight chunks into a shared-memory ring (cp.async.bulk, TMA engine).
-//   warps 1..16 (512 threads)  two threads per pair row of a SET of two 128-row tiles (warp w: tile ((w-1)/4)%2, TMEM
-//                              lane quarter w%4, unit half (w-1)/8): they build the row, run layer 0 on the CUDA
-//                              cores, write the A operand, and later do the epilogue.
+//   warp 9 (one elected lane)  streams the fc1 weight chunks into a shared-memory ring (cp.async.bulk, TMA engine).
+//   warps 1..8 (256 threads)   producers.  A SET is two 128-row tiles; thread (lane quarter w%4, unit half (w-1)/4)
+//                              owns row r of BOTH tiles (same TMEM lane, different columns) and half of the units of a
+//                              stage: the two rows ride in the two halves of the packed fp32 instructions, so every
+//                              layer-0 weight fetched from shared memory serves two rows.  The same threads build the
+//                              rows and later do the epilogue.
 // The roles meet only through mbarriers (A-ready / B-full / stage-free / accumulators-full / accumulators-free) over
 // 4-stage rings with a static schedule; there is no CTA-wide barrier inside a set.
 // The 384 -> 128 layer is a [128 x 384] x [384 x 128] GEMM per tile, fp32 accumulators in tensor memory.
@@ -36,8 +38,8 @@
 #define TC_WAIT_HINT 20000u
 #endif
 #define TC_SET 2             // tiles per set = accumulators in tensor memory (2 x 128 columns)
-#define TC_NP 512            // producer / epilogue threads (warps 1 .. 16), two per pair row
-#define TC_NT (TC_NP + 64)   // + warp 0 = MMA issue, warp 17 = fc1 chunk loader (TMA)
+#define TC_NP 256            // producer / epilogue threads (warps 1 .. 8): row r of both tiles x half of the units
+#define TC_NT (TC_NP + 64)   // + warp 0 = MMA issue, warp 9 = fc1 chunk loader (TMA)
 #define TC_H 128
 #define TC_H3 384
 #define TC_KC 16             // hidden units per ring stage = two MMA K-slices
@@ -208,7 +210,7 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
   const int n = P.n, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool producer = warp >= 1 && warp <= TC_NP / 32;   // warp 0 = MMA issue, last warp = weight loader
   // producers: hardware warp w may only touch TMEM lanes 32*(w%4)..+31, so rows follow the warp id
-  const int row = 32 * (warp & 3) + lane, mytile = ((warp - 1) >> 2) & 1, half = (warp - 1) >> 3, pt = tid - 32;
+  const int row = 32 * (warp & 3) + lane, half = (warp - 1) >> 2, pt = tid - 32;
   float *s_obs = reinterpret_cast<float *>(smem + TcSmem::obs);
   double *s_raw = reinterpret_cast<double *>(smem + TcSmem::raw);
   uint64_t *s_nbr = reinterpret_cast<uint64_t *>(smem + TcSmem::nbr);
@@ -341,38 +343,44 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
       }
     } else {
       // =============================== producers: rows, layer 0, epilogue ===============================
+      const uint32_t lane_base = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
       for (int set = 0; set < nsets; set++, t++) {
-        const int p = (set * TC_SET + mytile) * 128 + row;   // this thread's pair row (shared with its partner warp)
-        const bool live = set * TC_SET + mytile < ntiles;    // warp-uniform: the tile exists
-        // ---- flat pair index -> (UAV a, its k-th neighbour b), x = la_a * la_b (uav.py:280-281)
-        float x[12];
-        if (p < npairs) {
-          int lo = 0, hi = A;  // largest a with off[a] <= p
-          while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= (uint32_t)p) lo = mid; else hi = mid; }
-          const int a = lo;
-          int k = p - (int)s_off[a];
-          uint64_t w = s_nbr[2 * a];
-          int base = (a / n) * n;
-          const int c0 = __popcll(w);
-          if (k >= c0) { k -= c0; w = s_nbr[2 * a + 1]; base += 64; }
-          for (int q = 0; q < k; q++) w &= w - 1;
-          const int b = base + __ffsll((long long)w) - 1;
+        const bool live1 = set * TC_SET + 1 < ntiles;  // warp-uniform: the set's second tile exists (the first always does)
+        // ---- this thread's two pair rows (row r of tile 0 and of tile 1): flat pair index -> (UAV a, its k-th
+        //      neighbour b), x = la_a * la_b (uav.py:280-281); the two rows are packed {row of tile 0, row of tile 1}
+        uint64_t xx[12];
+        {
+          float x0[12], x1[12];
+          auto build = [&](const int p, float *x) {
+            if (p < npairs) {
+              int lo = 0, hi = A;  // largest a with off[a] <= p
+              while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= (uint32_t)p) lo = mid; else hi = mid; }
+              const int a = lo;
+              int k = p - (int)s_off[a];
+              uint64_t w = s_nbr[2 * a];
+              int base = (a / n) * n;
+              const int c0 = __popcll(w);
+              if (k >= c0) { k -= c0; w = s_nbr[2 * a + 1]; base += 64; }
+              for (int q = 0; q < k; q++) w &= w - 1;
+              const int b = base + __ffsll((long long)w) - 1;
 #pragma unroll
-          for (int q = 0; q < 12; q++) x[q] = s_obs[a * 12 + q] * s_obs[b * 12 + q];
-        } else {
+              for (int q = 0; q < 12; q++) x[q] = s_obs[a * 12 + q] * s_obs[b * 12 + q];
+            } else {
 #pragma unroll
-          for (int q = 0; q < 12; q++) x[q] = 0.f;
+              for (int q = 0; q < 12; q++) x[q] = 0.f;
+            }
+          };
+          build((set * TC_SET) * 128 + row, x0);
+          build((set * TC_SET + 1) * 128 + row, x1);
+#pragma unroll
+          for (int q = 0; q < 12; q++) xx[q] = tc_pack2(x0[q], x1[q]);
         }
 
-        uint64_t xx[12];  // {x, x}: the broadcast operand of the packed FMAs
-#pragma unroll
-        for (int q = 0; q < 12; q++) xx[q] = tc_pack2(x[q], x[q]);
-
-        // ---- layer 0 per ring stage of 16 hidden units; this thread computes the 8 units of K-slice `half` of its
-        //      row and writes them (hi and lo) into the stage's tensor-memory columns.  The three input branches
+        // ---- layer 0 per ring stage of 16 hidden units; this thread computes the 8 units of K-slice `half` for its
+        //      two rows and writes them (hi and lo) into the stage's tensor-memory columns.  The three input branches
         //      (communication 5, observation 4, boundary/state 3 inputs; PMINet.py:45-58, BN folded) are unrolled
-        //      so the row stays in registers; each branch covers 8 chunks.
-        const uint32_t a_lane = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + TC_ACOL0 + 32u * (uint32_t)mytile + 8u * (uint32_t)half;
+        //      so the rows stay in registers; each branch covers 8 chunks.
+        const uint32_t a_lane = lane_base + TC_ACOL0 + 8u * (uint32_t)half;
         auto run_chunk = [&](const int c, const uint64_t *xin, const int dim) {
           const uint32_t s = c % TC_NS, c4 = c / TC_NS;
           if (t > 0 || c4 > 0) {  // MMAs that read this stage have completed
@@ -382,27 +390,34 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
 #ifdef TC_ABL_NOPROD
           if (c < 0)
 #endif
-          if (live) {
-            float hv[8], lv[8];
+          {
+            float h0[8], l0[8], h1[8], l1[8];
 #pragma unroll
-            for (int e = 0; e < 8; e += 2) {  // two units per packed fp32 instruction (FFMA2)
+            for (int e = 0; e < 8; e += 2) {  // unit pair (u, u'): weights interleaved {b b' w0 w0' | w1 w1' w2 w2' | w3 w3' w4 w4'}
               const float4 *wp = reinterpret_cast<const float4 *>(s_w0 + ((c * TC_KC + half * 8 + e) >> 1) * 12);
-              const float4 q0 = wp[0], q1 = wp[1];  // b b' w0 w0' | w1 w1' w2 w2'
-              uint64_t acc = tc_pack2(q0.x, q0.y);
-              acc = tc_fma2(tc_pack2(q0.z, q0.w), xin[0], acc);
-              acc = tc_fma2(tc_pack2(q1.x, q1.y), xin[1], acc);
-              acc = tc_fma2(tc_pack2(q1.z, q1.w), xin[2], acc);
+              const float4 q0 = wp[0], q1 = wp[1];
+              uint64_t acc = tc_pack2(q0.x, q0.x), acc2 = tc_pack2(q0.y, q0.y);     // {row 0, row 1} of unit u / u'
+              acc = tc_fma2(tc_pack2(q0.z, q0.z), xin[0], acc);   acc2 = tc_fma2(tc_pack2(q0.w, q0.w), xin[0], acc2);
+              acc = tc_fma2(tc_pack2(q1.x, q1.x), xin[1], acc);   acc2 = tc_fma2(tc_pack2(q1.y, q1.y), xin[1], acc2);
+              acc = tc_fma2(tc_pack2(q1.z, q1.z), xin[2], acc);   acc2 = tc_fma2(tc_pack2(q1.w, q1.w), xin[2], acc2);
               if (dim > 3) {
-                const float4 q2 = wp[2];            // w3 w3' | w4 w4'
-                acc = tc_fma2(tc_pack2(q2.x, q2.y), xin[3], acc);
-                if (dim > 4) acc = tc_fma2(tc_pack2(q2.z, q2.w), xin[4], acc);
+                const float4 q2 = wp[2];
+                acc = tc_fma2(tc_pack2(q2.x, q2.x), xin[3], acc); acc2 = tc_fma2(tc_pack2(q2.y, q2.y), xin[3], acc2);
+                if (dim > 4) { acc = tc_fma2(tc_pack2(q2.z, q2.z), xin[4], acc); acc2 = tc_fma2(tc_pack2(q2.w, q2.w), xin[4], acc2); }
               }
-              const float a0 = fmaxf(__uint_as_float((uint32_t)acc), 0.f), a1 = fmaxf(__uint_as_float((uint32_t)(acc >> 32)), 0.f);
-              hv[e] = tf32_rna(a0); hv[e + 1] = tf32_rna(a1);
-              lv[e] = tf32_rna(a0 - hv[e]); lv[e + 1] = tf32_rna(a1 - hv[e + 1]);
+              const float a00 = fmaxf(__uint_as_float((uint32_t)acc), 0.f), a01 = fmaxf(__uint_as_float((uint32_t)(acc >> 32)), 0.f);
+              const float a10 = fmaxf(__uint_as_float((uint32_t)acc2), 0.f), a11 = fmaxf(__uint_as_float((uint32_t)(acc2 >> 32)), 0.f);
+              h0[e] = tf32_rna(a00); l0[e] = tf32_rna(a00 - h0[e]);              // unit u,  tile 0
+              h1[e] = tf32_rna(a01); l1[e] = tf32_rna(a01 - h1[e]);              // unit u,  tile 1
+              h0[e + 1] = tf32_rna(a10); l0[e + 1] = tf32_rna(a10 - h0[e + 1]);  // unit u', tile 0
+              h1[e + 1] = tf32_rna(a11); l1[e + 1] = tf32_rna(a11 - h1[e + 1]);  // unit u', tile 1
             }
-            tmem_st8(a_lane + TC_ACOLS * s, hv);
-            tmem_st8(a_lane + TC_ACOLS * s + 16u, lv);
+            tmem_st8(a_lane + TC_ACOLS * s, h0);
+            tmem_st8(a_lane + TC_ACOLS * s + 16u, l0);
+            if (live1) {
+              tmem_st8(a_lane + TC_ACOLS * s + 32u, h1);
+              tmem_st8(a_lane + TC_ACOLS * s + 48u, l1);
+            }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           }
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -419,23 +434,34 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
         // ---- epilogue: bias + ReLU + fc2 (PMINet.py:59-62); the two threads of a row take 64 accumulator columns each
         mbar_wait(bar_accfull, t & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float part = 0.f;
-        if (live) {
-#pragma unroll 1
-          for (int cb = half * 64; cb < half * 64 + 64; cb += 32) {
-            float v[32];
-            tmem_ld32(tmem_d + 128u * (uint32_t)mytile + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)cb, v);
+        float part[TC_SET] = {0.f, 0.f};
 #pragma unroll
-            for (int k = 0; k < 32; k++) part = fmaf(s_w2[cb + k], fmaxf(v[k] + s_b1[cb + k], 0.f), part);
+        for (int q = 0; q < TC_SET; q++) {
+          if (q == 0 || live1) {
+#pragma unroll 1
+            for (int cb = half * 64; cb < half * 64 + 64; cb += 32) {
+              float v[32];
+              tmem_ld32(lane_base + 128u * (uint32_t)q + (uint32_t)cb, v);
+              float acc = part[q];
+#pragma unroll
+              for (int k = 0; k < 32; k++) acc = fmaf(s_w2[cb + k], fmaxf(v[k] + s_b1[cb + k], 0.f), acc);
+              part[q] = acc;
+            }
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_accfree);  // this warp's rows have left tensor memory
-        // combine the two halves of each row (producer-only named barrier: warps 0 and 17 are elsewhere)
-        if (half) s_part[mytile * 128 + row] = part;
+        // combine the two halves of each row (producer-only named barrier: warps 0 and 9 are elsewhere)
+        if (half) { s_part[row] = part[0]; s_part[128 + row] = part[1]; }
         asm volatile("bar.sync 1, %0;" ::"n"(TC_NP) : "memory");
-        if (!half && p < npairs) s_logit[p] = (part + s_part[mytile * 128 + row]) + W.b2;
+        if (!half) {
+#pragma unroll
+          for (int q = 0; q < TC_SET; q++) {
+            const int p = (set * TC_SET + q) * 128 + row;
+            if (p < npairs) s_logit[p] = (part[q] + s_part[q * 128 + row]) + W.b2;
+          }
+        }
         asm volatile("bar.sync 1, %0;" ::"n"(TC_NP) : "memory");
       }
     }
