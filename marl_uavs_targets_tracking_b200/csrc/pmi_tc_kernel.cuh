@@ -344,37 +344,38 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
     } else {
       // =============================== producers: rows, layer 0, epilogue ===============================
       const uint32_t lane_base = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
+      // this thread's two pair rows of a set (row r of tile 0 and of tile 1): flat pair index -> (UAV a, its k-th
+      // neighbour b), x = la_a * la_b (uav.py:280-281); the two rows are packed {row of tile 0, row of tile 1}
+      uint64_t xx[12];
+      auto build_rows = [&](const int set) {
+        float x0[12], x1[12];
+        auto build = [&](const int p, float *x) {
+          if (p < npairs) {
+            int lo = 0, hi = A;  // largest a with off[a] <= p
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= (uint32_t)p) lo = mid; else hi = mid; }
+            const int a = lo;
+            int k = p - (int)s_off[a];
+            uint64_t w = s_nbr[2 * a];
+            int base = (a / n) * n;
+            const int c0 = __popcll(w);
+            if (k >= c0) { k -= c0; w = s_nbr[2 * a + 1]; base += 64; }
+            for (int q = 0; q < k; q++) w &= w - 1;
+            const int b = base + __ffsll((long long)w) - 1;
+#pragma unroll
+            for (int q = 0; q < 12; q++) x[q] = s_obs[a * 12 + q] * s_obs[b * 12 + q];
+          } else {
+#pragma unroll
+            for (int q = 0; q < 12; q++) x[q] = 0.f;
+          }
+        };
+        build((set * TC_SET) * 128 + row, x0);
+        build((set * TC_SET + 1) * 128 + row, x1);
+#pragma unroll
+        for (int q = 0; q < 12; q++) xx[q] = tc_pack2(x0[q], x1[q]);
+      };
+      if (nsets > 0) build_rows(0);
       for (int set = 0; set < nsets; set++, t++) {
         const bool live1 = set * TC_SET + 1 < ntiles;  // warp-uniform: the set's second tile exists (the first always does)
-        // ---- this thread's two pair rows (row r of tile 0 and of tile 1): flat pair index -> (UAV a, its k-th
-        //      neighbour b), x = la_a * la_b (uav.py:280-281); the two rows are packed {row of tile 0, row of tile 1}
-        uint64_t xx[12];
-        {
-          float x0[12], x1[12];
-          auto build = [&](const int p, float *x) {
-            if (p < npairs) {
-              int lo = 0, hi = A;  // largest a with off[a] <= p
-              while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= (uint32_t)p) lo = mid; else hi = mid; }
-              const int a = lo;
-              int k = p - (int)s_off[a];
-              uint64_t w = s_nbr[2 * a];
-              int base = (a / n) * n;
-              const int c0 = __popcll(w);
-              if (k >= c0) { k -= c0; w = s_nbr[2 * a + 1]; base += 64; }
-              for (int q = 0; q < k; q++) w &= w - 1;
-              const int b = base + __ffsll((long long)w) - 1;
-#pragma unroll
-              for (int q = 0; q < 12; q++) x[q] = s_obs[a * 12 + q] * s_obs[b * 12 + q];
-            } else {
-#pragma unroll
-              for (int q = 0; q < 12; q++) x[q] = 0.f;
-            }
-          };
-          build((set * TC_SET) * 128 + row, x0);
-          build((set * TC_SET + 1) * 128 + row, x1);
-#pragma unroll
-          for (int q = 0; q < 12; q++) xx[q] = tc_pack2(x0[q], x1[q]);
-        }
 
         // ---- layer 0 per ring stage of 16 hidden units; this thread computes the 8 units of K-slice `half` for its
         //      two rows and writes them (hi and lo) into the stage's tensor-memory columns.  The three input branches
@@ -430,6 +431,9 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
         for (int cc = 8; cc < 16; cc++) run_chunk(cc, xx + 5, 4);
 #pragma unroll 1
         for (int cc = 16; cc < 24; cc++) run_chunk(cc, xx + 9, 3);
+
+        // the rows of the next set are built while the tensor pipe drains the last stages of this one
+        if (set + 1 < nsets) build_rows(set + 1);
 
         // ---- epilogue: bias + ReLU + fc2 (PMINet.py:59-62); the two threads of a row take 64 accumulator columns each
         mbar_wait(bar_accfull, t & 1);
