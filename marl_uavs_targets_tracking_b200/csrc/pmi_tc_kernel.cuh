@@ -49,8 +49,8 @@
 #define TC_STAGE_BYTES (2 * TC_A_BYTES)  // B_hi + B_lo = 16 KB
 #define TC_ACOL0 256u        // first TMEM column of the A ring
 #define TC_ACOLS 64u         // TMEM columns per A stage: 2 tiles x (16 hi + 16 lo)
-#define TC_AMAX 256          // UAVs per environment group
-#define TC_PMAX 8192         // neighbour pairs per environment group
+#define TC_AMAX 512          // UAVs per environment group
+#define TC_PMAX 16384        // neighbour pairs per environment group (logits stay in shared memory until the softmax)
 
 // instruction descriptor: D = F32, A = B = TF32, K-major both, N = 128 (>>3 at bit 17), M = 128 (>>4 at bit 24)
 #define TC_IDESC ((1u << 4) | (2u << 7) | (2u << 10) | ((TC_H >> 3) << 17) | ((128u >> 4) << 24))
@@ -272,7 +272,7 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
       s_off[a + 1] = __popcll(n0) + __popcll(n1);
     }
     __syncthreads();
-    if (warp == 1) {  // exclusive scan of the neighbour counts (A <= 256): 8 per lane + warp scan
+    if (warp == 1) {  // exclusive scan of the neighbour counts (A <= 512): 16 per lane + warp scan
       const int per = (A + 31) / 32, lo = lane * per;
       uint32_t sum = 0;
       for (int k = 0; k < per; k++) if (lo + k < A) sum += s_off[lo + k + 1];
