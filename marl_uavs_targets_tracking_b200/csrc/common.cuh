@@ -79,6 +79,7 @@ struct uavsim {
   int pmi_g, pmi_pmax, pmi_tm, pmi_grid_max;
   // tensor-core path (H = 128): fc1 pre-split into UMMA tiles
   bool has_tc;
+  bool has_cc;   // the fp32 CUDA-core PMI kernel fits this shape (its pair buffer is 8 192 rows; n > 91 needs the tensor path)
   int pmi_path;        // 0 auto, 1 CUDA cores, 2 tensor cores
   float *d_tc_tiles;   // [12][2][128*32]
   int tc_g;

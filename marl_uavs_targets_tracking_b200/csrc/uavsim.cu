@@ -343,6 +343,11 @@ static int pmi_tc_launch(uavsim_t *h, int64_t e0, int64_t cnt, double coop, cuda
 
 static int pmi_launch(uavsim_t *h, int64_t e0, int64_t cnt, double coop, cudaStream_t st, bool configure_only) {
   if (!configure_only && pmi_use_tensor(h)) return pmi_tc_launch(h, e0, cnt, coop, st);
+  if (!configure_only && !h->has_cc) {
+    SET_ERR("PMI mode: n_uav=%d is too large for the CUDA-core PMI kernel and the tensor path is %s", h->kp.n,
+            h->pmi_path == 1 ? "switched off (uavsim_set_pmi_path 1)" : "unavailable (hidden != 128)");
+    return UAVSIM_ERR_UNSUPPORTED;
+  }
   switch (h->pmi.H) {
     case 32: return pmi_launch_t<2, 64>(h, e0, cnt, coop, st, configure_only);
     case 64: return pmi_launch_t<4, 64>(h, e0, cnt, coop, st, configure_only);
@@ -393,9 +398,9 @@ extern "C" int uavsim_set_pmi_weights(uavsim_t *h, const UavSimPmiWeights *w, vo
   h->pmi.w2 = h->pmi.b1 + n_b1;
   h->pmi.b2 = w->b2;
   int rc = pmi_configure(h);
-  if (rc) return rc;
-  rc = pmi_launch(h, 0, 0, 0.0, st, true);
-  if (rc) return rc;
+  if (!rc) rc = pmi_launch(h, 0, 0, 0.0, st, true);
+  h->has_cc = rc == 0;
+  if (rc && H != TC_H) return rc;  // only the tensor path (hidden = 128) can take over a shape the CUDA-core kernel cannot hold
   h->has_tc = false;
   if (H == TC_H) {
     // tensor-core path: fc1 split hi/lo (TF32) and laid out as the K-major UMMA tiles the kernel bulk-copies:

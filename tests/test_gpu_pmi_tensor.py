@@ -92,3 +92,29 @@ def test_tensor_path_unsupported_sizes_fall_back_or_fail_loudly():
     with pytest.raises(UavSimError):
         env.set_pmi_path(2)                # tensor path demanded but hidden != 128
     env.close()
+
+
+def test_tensor_path_serves_swarms_the_cuda_core_kernel_cannot_hold(oracle):
+    """n = 128 (UAVSIM_MAX_UAV): 16 256 ordered pairs per environment exceed the CUDA-core kernel's 8 192-row pair
+    buffer; the tensor path takes the shape, and asking for the CUDA-core path fails loudly instead of falling back."""
+    from marl_uavs_targets_tracking_b200 import UavSimError, default_config
+    n, m, E, T = 128, 5, 3, 4
+    cfg = default_config("MAAC-R", n, m)
+    pmi = _pmi()
+    env = _env(n, m, cfg, E, seed=21)
+    env.reset(cfg)
+    P = oracle_params_from_config(cfg, n, m)
+    opmi = oracle_pmi_from_module(pmi)
+    st = {k: np.ascontiguousarray(v.cpu().numpy()) for k, v in env.get_state().items()}
+    worst = 0.0
+    for t in range(T):
+        a = env.random_actions(5, t).cpu().numpy().copy()
+        ref = oracle.step_batch(P, 2, float(cfg["cooperative"]), opmi, st, a, nthreads=8)
+        _, rew4, _ = env.step_device(cfg, pmi)
+        worst = max(worst, max_scaled_err(rew4[0].double().cpu().numpy(), ref["rew4"][0]))
+    print("n=128 tensor path", worst)
+    assert worst <= TOL_TC
+    env.set_pmi_path(1)
+    with pytest.raises(UavSimError):
+        env.step_device(cfg, pmi)
+    env.close()
