@@ -80,9 +80,6 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
 // bounded wait: a barrier that never completes (a descriptor bug) traps instead of hanging the GPU.  The suspend-time
 // hint lets the hardware park the warp until the phase completes instead of re-polling: spinning producers would
 // otherwise take issue slots from the MMA warp and from the producers that still have work.
@@ -91,11 +88,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   for (uint32_t spin = 0; !done; spin++) {
     asm volatile(
         "{\n\t.reg .pred P1;\n\t"
-#ifdef TC_WAIT_NOHINT
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-#else
         "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
-#endif
         "selp.b32 %0, 1, 0, P1;\n\t}"
         : "=r"(done)
         : "r"(bar), "r"(parity), "r"(TC_WAIT_HINT)
@@ -103,45 +96,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (spin > (1u << 22)) __trap();
   }
 }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   // K-major, no swizzle: start address, LBO = 2048 B (between the two 16-byte K halves of an MMA),
   // SBO = 128 B (between 8-row groups), descriptor version 1 (Blackwell)
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(2048u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) |
          (1ull << 46);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(TC_IDESC), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// The control warp runs its loop with all 32 lanes converged (warp-uniform control flow and operands, so the
-// descriptors live in uniform registers) and predicates the single-thread instructions on an elected lane INSIDE the
+// The MMA warp and the loader warp run their loops with all 32 lanes converged (warp-uniform control flow and operands,
+// so descriptors and addresses live in uniform registers) and predicate the single-thread instructions on an elected lane INSIDE the
 // asm: a divergent `if (lane == 0)` around them makes the compiler wrap every tcgen05.mma in an ELECT / R2UR waterfall
-// loop, ~16 issue slots per MMA, which made the one issuing thread the bottleneck of the kernel.
+// loop, ~16 issue slots per MMA, which made the one issuing thread the bottleneck of the kernel.  TC_ABL_* are
+// profiling switches (one MMA per K-slice / no layer-0 work) used for the ablations quoted in DESIGN.md.
 __device__ __forceinline__ uint32_t elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
   return pred;
-}
-__device__ __forceinline__ void umma_tf32_p(uint32_t lead, uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(TC_IDESC), "r"(accumulate), "r"(lead)
-      : "memory");
 }
 // D[tmem] (+)= A[tmem] * B[smem]: the A operand read from tensor memory (lane = row, one column per tf32 element)
 __device__ __forceinline__ void umma_tf32_ts_p(uint32_t lead, uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t accumulate) {
