@@ -36,6 +36,7 @@ struct KParams {
   double dt, uav_h_max;       // for actions outside the precomputed table
   double dc, dp, two_dp;      // two_dp = radio*dp, radio = 2 (src/agent/uav.py:214)
   double tv, uv;              // target / uav v_max
+  double tv_over_uv;
   double s_dp_le, s_dp_lt, s_dc_le, s_2dp_le;  // exact squared thresholds
   double alpha, beta, gamma;
   double tt_hi;               // 2*m_targets            (src/environment.py:207-208)

@@ -69,25 +69,30 @@ struct CtaSmem {
 static size_t step_smem_bytes(int n, int m, int na, int epb) {
   const EnvLayout L = env_layout(n, m);
   size_t b = (size_t)epb * L.stride;
-  b += ((size_t)epb * n + 3 * (size_t)na + 64) * 8 + 8;
-  b += (size_t)epb * n * 12 * 4;
-  b += ((size_t)epb * m + 2 * (size_t)epb) * 4;
+  b += ((size_t)epb * n + 64) * 8 + 8;          // raw, red (+ pad)
+  b += (size_t)epb * n * 12 * 4;                // obs
+  b += ((size_t)epb * m + 2 * (size_t)epb) * 4 + 4;  // tcnt, far, cov (+ pad)
+  b += 3 * (size_t)na * 8;                      // dth
   return b + 16;
 }
 
+// The per-action table (the only run-time sized array) comes last, so with compile-time n, m and epb every other
+// offset is a constant.
 __device__ __forceinline__ CtaSmem carve(unsigned char *base, int n, int m, int na, int epb, int stride) {
   CtaSmem s;
   s.env = base;
   double *d = reinterpret_cast<double *>(base + (size_t)epb * stride);  // stride is a multiple of 16
   s.raw = d; d += (size_t)epb * n;
-  s.dth = d; d += 3 * na;
   s.red = d; d += 64;
-  d += ((size_t)epb * n + 3 * (size_t)na) & 1;  // keep obs 16-byte aligned (plain pointer arithmetic: stays shared)
+  d += ((size_t)epb * n) & 1;  // keep obs 16-byte aligned (plain pointer arithmetic: stays shared)
   s.obs = reinterpret_cast<float *>(d);
   int *ip = reinterpret_cast<int *>(s.obs + (size_t)epb * n * 12);
   s.tcnt = ip; ip += (size_t)epb * m;
   s.far = ip; ip += epb;
-  s.cov = ip;
+  s.cov = ip; ip += epb;
+  ip += ((size_t)epb * m) & 1;  // 8-byte alignment for the doubles that follow
+  s.dth = reinterpret_cast<double *>(ip);
+  (void)na;
   return s;
 }
 
@@ -458,10 +463,11 @@ __device__ __forceinline__ void agent_fast(const KParams &P, const UavSimBuffers
 template <int CN, int CM, bool MASKS, int NT>
 __global__ void __launch_bounds__(NT, UAVSIM_WARPS_PER_SM * 32 / NT)
 uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restrict__ g_dth, int64_t env_begin,
-                   int64_t env_count, int epb, int mode, double coop, int done_flag,
+                   int64_t env_count, int epb_rt, int mode, double coop, int done_flag,
                    double *__restrict__ stats_partial) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = CN ? CN : P.n, m = CM ? CM : P.m;
+  const int epb = CN ? NT / CN : epb_rt;  // environments per CTA: the host passes NT / n, a constant when n is
   constexpr bool WARP_ENV = (CN > 0) && (CN % 32 == 0);
   const EnvLayout L = (CN && CM) ? env_layout(CN, CM) : env_layout(n, m);
   const int tid = threadIdx.x;
@@ -507,7 +513,7 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
       B.tx[gi] = x; B.ty[gi] = y;
       V.tpos()[t] = make_double2(x, y);
       // cos(target.h) * target.v_max / self.v_max  (src/agent/uav.py:115-116)
-      V.tvel()[t] = make_double2(ch * P.tv / P.uv, sh * P.tv / P.uv);
+      V.tvel()[t] = make_double2(ch * P.tv_over_uv, sh * P.tv_over_uv);  // fp32 outputs: the ratio is exact enough
       EnvView::put_pair(V.tposf(), t, (float)(x - P.cx), (float)(y - P.cy));
       if (!(fabs(x - P.cx) <= P.rmax && fabs(y - P.cy) <= P.rmax)) S.far[te] = 1;
       S.tcnt[q] = 0;

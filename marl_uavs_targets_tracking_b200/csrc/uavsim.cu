@@ -99,7 +99,7 @@ extern "C" int uavsim_create(const UavSimParams *p, int64_t n_envs, int64_t env_
   k.dt = p->dt; k.uav_h_max = p->uav_h_max;
   k.dtv_t = p->dt * p->tgt_v_max;
   k.dc = p->dc; k.dp = p->dp; k.two_dp = 2 * p->dp;
-  k.tv = p->tgt_v_max; k.uv = p->uav_v_max;
+  k.tv = p->tgt_v_max; k.uv = p->uav_v_max; k.tv_over_uv = p->tgt_v_max / p->uav_v_max;
   k.s_dp_le = exact_sq_threshold(p->dp, false);
   k.s_dp_lt = exact_sq_threshold(p->dp, true);
   k.s_dc_le = exact_sq_threshold(p->dc, false);
@@ -137,8 +137,12 @@ extern "C" int uavsim_create(const UavSimParams *p, int64_t n_envs, int64_t env_
   else { h->nt = 128; h->step_fn[0] = uavsim_step_kernel<0, 0, false, 128>; h->step_fn[1] = uavsim_step_kernel<0, 0, true, 128>; }
   int epb = h->nt / p->n_uav;
   if (epb < 1) epb = 1;
-  if ((int64_t)epb > n_envs) epb = (int)n_envs;
-  while (epb > 1 && step_smem_bytes(k.n, k.m, k.na, epb) > 64 * 1024) epb--;
+  // the compile-time instances derive nt / n themselves (constant shared-memory offsets); run-time sizes adapt
+  const bool fixed_shape = (k.n == 64 && k.m == 64) || (k.n == 10 && k.m == 10);
+  if (!fixed_shape) {
+    if ((int64_t)epb > n_envs) epb = (int)n_envs;
+    while (epb > 1 && step_smem_bytes(k.n, k.m, k.na, epb) > 64 * 1024) epb--;
+  }
   h->epb = epb;
   h->smem_step = step_smem_bytes(k.n, k.m, k.na, epb);
   if (h->smem_step > 227 * 1024) {
