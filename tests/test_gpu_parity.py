@@ -276,12 +276,14 @@ def test_sharding_is_invisible_in_the_results():
         e.close()
 
 
-@pytest.mark.parametrize("method", ["MAAC-G", "MAAC-R"])
-def test_host_buffer_step_equals_device_step(method):
+@pytest.mark.parametrize("method,hidden", [("MAAC-G", 0), ("MAAC-R", 64), ("MAAC-R", 128)])
+def test_host_buffer_step_equals_device_step(method, hidden):
+    """uavsim_step_host pipelines env ranges over streams; hidden = 64 takes the CUDA-core PMI kernel, 128 the tensor
+    kernel (env_begin / env_count of a chunk must land on the same rows as the whole-batch launch)."""
     from marl_uavs_targets_tracking_b200 import PMINetwork, default_config
     cfg = default_config(method, 10, 10)
     torch.manual_seed(0)
-    pmi = PMINetwork(hidden_dim=64).eval() if method == "MAAC-R" else None
+    pmi = PMINetwork(hidden_dim=hidden).eval() if method == "MAAC-R" else None
     E = 1000
     a_env, b_env = _env(10, 10, cfg, E, seed=8), _env(10, 10, cfg, E, seed=8)
     a_env.reset(cfg); b_env.reset(cfg)
