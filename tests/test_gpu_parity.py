@@ -223,6 +223,39 @@ def test_long_episode_64x64_does_not_stall():
     env.close()
 
 
+def test_headline_batch_sampled_against_the_oracle(oracle):
+    """BASELINE.json configs[3] at full size (64x64, 65 536 environments): 96 environments spread over the batch are
+    replayed in the CPU oracle for a whole 200-step episode -- covered / tracker counts bit-exact every step, state,
+    observation and rewards within tolerance -- so the full-size launch geometry (persistent grid, grid-stride over
+    environments, last partial wave) is checked against the reference semantics, not only against itself."""
+    from marl_uavs_targets_tracking_b200 import default_config
+    n = m = 64
+    E, T = 65536, 200
+    cfg = default_config("MAAC-G", n, m)
+    env = _env(n, m, cfg, E, seed=123, track_counts=True)
+    env.reset(cfg)
+    ids = np.unique(np.concatenate([np.arange(0, E, 701), [E - 1, E - 2, 2367, 2368, 2369]]))[:96]
+    idx = torch.as_tensor(ids, device="cuda:0")
+    P = oracle_params_from_config(cfg, n, m)
+    st = {k: np.ascontiguousarray(v[idx].cpu().numpy()) for k, v in env.get_state().items()}
+    worst_o = worst_r = worst_s = 0.0
+    for t in range(T):
+        a = env.random_actions(31, t)[idx].cpu().numpy().copy()
+        obs, rew4, cov = env.step_device(cfg, None)
+        ref = oracle.step_batch(P, 1, float(cfg["cooperative"]), None, st, a, nthreads=8)
+        assert np.array_equal(cov[idx].cpu().numpy(), ref["covered"]), t
+        assert np.array_equal(env.tracker_counts[idx].cpu().numpy(), ref["tracker_cnt"]), t
+        worst_o = max(worst_o, max_scaled_err(obs[idx].double().cpu().numpy(), ref["obs"]))
+        worst_r = max(worst_r, max_scaled_err(rew4[:, idx].double().cpu().numpy(), ref["rew4"]))
+    gs = env.get_state()
+    for k in ("ux", "uy", "uh", "tx", "ty", "th"):
+        worst_s = max(worst_s, max_scaled_err(gs[k][idx].cpu().numpy(), st[k]))
+    assert np.array_equal(gs["ua"][idx].cpu().numpy(), st["ua"])
+    print("full-size sample: obs %.1e rewards %.1e state %.1e" % (worst_o, worst_r, worst_s))
+    assert worst_o <= 1e-6 and worst_r <= 1e-6 and worst_s <= 1e-11
+    env.close()
+
+
 def test_reset_and_random_policy_match_philox_reference():
     from marl_uavs_targets_tracking_b200 import default_config
     from philox_ref import actions_reference, reset_reference

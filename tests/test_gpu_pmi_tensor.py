@@ -118,3 +118,31 @@ def test_tensor_path_serves_swarms_the_cuda_core_kernel_cannot_hold(oracle):
     with pytest.raises(UavSimError):
         env.step_device(cfg, pmi)
     env.close()
+
+
+def test_configs2_batch_sampled_against_the_oracle(oracle):
+    """BASELINE.json configs[2] at full size (default scenario, 16 384 environments, MAAC-R, hidden 128): 64 environments
+    spread over the batch replayed in the CPU oracle for 80 steps; the reward goes through the tensor-core kernel."""
+    from marl_uavs_targets_tracking_b200 import default_config
+    n = m = 10
+    E, T = 16384, 80
+    cfg = default_config("MAAC-R", n, m)
+    pmi = _pmi(seed=4)
+    env = _env(n, m, cfg, E, seed=77)
+    env.reset(cfg)
+    ids = np.unique(np.concatenate([np.arange(0, E, 263), [E - 1, 7399, 7400]]))[:64]
+    idx = torch.as_tensor(ids, device="cuda:0")
+    P = oracle_params_from_config(cfg, n, m)
+    opmi = oracle_pmi_from_module(pmi)
+    st = {k: np.ascontiguousarray(v[idx].cpu().numpy()) for k, v in env.get_state().items()}
+    worst = 0.0
+    for t in range(T):
+        a = env.random_actions(3, t)[idx].cpu().numpy().copy()
+        obs, rew4, cov = env.step_device(cfg, pmi)
+        ref = oracle.step_batch(P, 2, float(cfg["cooperative"]), opmi, st, a, nthreads=8)
+        assert np.array_equal(cov[idx].cpu().numpy(), ref["covered"]), t
+        worst = max(worst, max_scaled_err(rew4[:, idx].double().cpu().numpy(), ref["rew4"]),
+                    max_scaled_err(obs[idx].double().cpu().numpy(), ref["obs"]))
+    print("configs[2] sample:", worst)
+    assert worst <= TOL_TC
+    env.close()
