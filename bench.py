@@ -329,7 +329,7 @@ def measure_training(torch, dist, env_cls, rank, world, device, steps=25, envs=6
     buf = PrioritizedReplayBuffer(1 << 24, device=device, seed=42)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     res = {}
-    for it in range(2):  # first pass warms the allocator and cuBLAS up
+    for it in range(3):  # the first passes warm the allocator and cuBLAS up; the last one is reported
         env.reset(cfg)
         if world > 1:
             dist.barrier()

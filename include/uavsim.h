@@ -197,6 +197,27 @@ int64_t uavsim_replay_launch_count(const uavsim_replay_t *h);
 int uavsim_replay_export(uavsim_replay_t *h, float *states, int32_t *actions, float *rewards, float *next_states,
                          float *priorities, float *probabilities, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused policy step of the batched rollout: probs = softmax(fc2(relu(fc1(obs)))) (FnnPolicyNet,
+ * src/models/actor_critic.py:85-99) and one categorical draw per row (ActorCritic.take_action,
+ * src/models/actor_critic.py:138-148) in one launch.  All pointers are DEVICE pointers, weights in torch layout.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t state_dim; /* 12 */
+  int32_t hidden;    /* <= 512 */
+  int32_t n_actions; /* 2 .. 16 */
+  int32_t _pad;
+  const float *w1;   /* fc1.weight [hidden, state_dim] */
+  const float *b1;   /* fc1.bias   [hidden] */
+  const float *w2;   /* fc2.weight [n_actions, hidden] */
+  const float *b2;   /* fc2.bias   [n_actions] */
+} UavSimPolicyWeights;
+
+/* actions[r] ~ Categorical(probs[r, :]) with the uniform Philox4x32-10 (seed; r, counter); probs [rows, n_actions] may be
+ * NULL.  obs [rows, 12] float32 (e.g. the environment's observation buffer). */
+int uavsim_policy_sample(const float *obs, int64_t rows, const UavSimPolicyWeights *w, uint64_t seed, uint64_t counter,
+                         int32_t *actions, float *probs, int device, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,6 +33,11 @@ class UavSimBuffers(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in _BUF_FIELDS]
 
 
+class UavSimPolicyWeights(C.Structure):
+    _fields_ = [("state_dim", C.c_int32), ("hidden", C.c_int32), ("n_actions", C.c_int32), ("_pad", C.c_int32),
+                ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p)]
+
+
 class UavSimPmiWeights(C.Structure):
     _fields_ = [("hidden", C.c_int32), ("_pad", C.c_int32), ("w0", C.c_void_p), ("b0", C.c_void_p),
                 ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_float), ("_pad2", C.c_float)]
@@ -59,6 +64,8 @@ SYMBOLS = {
     "uavsim_episode_stats": (C.c_int, [_H, C.POINTER(C.c_double), C.c_void_p]),
     "uavsim_launch_count": (C.c_int64, [_H]),
     "uavsim_step_count": (C.c_int64, [_H]),
+    "uavsim_policy_sample": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(UavSimPolicyWeights), C.c_uint64, C.c_uint64,
+                                       C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     # prioritized replay (src/train.py:73-139)
     "uavsim_replay_create": (C.c_int, [C.c_int64, C.c_int, C.c_double, C.c_int, C.POINTER(_H)]),
     "uavsim_replay_destroy": (C.c_int, [_H]),

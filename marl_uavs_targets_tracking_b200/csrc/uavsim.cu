@@ -59,6 +59,8 @@ static float prefilter_threshold(double thr, double rmax) {
   return nextafterf(f, INFINITY);
 }
 
+#include "policy.cuh"
+
 extern "C" int uavsim_abi_version(void) { return UAVSIM_ABI_VERSION; }
 extern "C" const char *uavsim_last_error(void) { return g_err; }
 extern "C" int64_t uavsim_launch_count(const uavsim_t *h) { return h ? h->launches : 0; }

@@ -269,6 +269,11 @@ class BatchedEnvironment:
             _cabi.check(self._lib.uavsim_step_host(self._h, mode, coop, ptr(h_actions), ptr(h_obs), ptr(h_rew4),
                                                    ptr(h_covered), int(chunks), self._stream()), "uavsim_step_host")
 
+    @property
+    def actions(self):
+        """The bound int32 [E,n] action buffer the next step_device(config, pmi) call reads."""
+        return self._actions
+
     def bind_actions(self, actions):
         """Point the kernel at another resident int32 [E,n] action tensor (no copy)."""
         assert actions.dtype == torch.int32 and actions.is_contiguous() and actions.numel() == self.n_envs * self.n_uav

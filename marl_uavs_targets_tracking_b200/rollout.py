@@ -6,10 +6,13 @@ forward, one on-device categorical sample and one `uavsim_step` launch; observat
 leave HBM.  The learner is stock PyTorch with the reference's architecture and one-step TD actor-critic update
 (src/models/actor_critic.py:85-179): it is the consumer of the accelerated path, not part of it.
 """
+import ctypes as C
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import _cabi
 from .distributed import episode_summary, reduce_episode_stats
 from .replay import PrioritizedReplayBuffer
 
@@ -38,11 +41,42 @@ class ValueNet(nn.Module):
         return self.fc2(F.relu(self.fc1(x))).squeeze(1)
 
 
+def fused_policy_sample(policy, states, seed, counter, want_probs=False, out=None):
+    """One launch of libuavsim's fused policy kernel (`uavsim_policy_sample`, csrc/policy.cuh): softmax(fc2(relu(fc1(x))))
+    and one categorical draw per row, uniforms from Philox4x32-10 keyed (seed; row, counter).  `policy` is a PolicyNet
+    (or a DDP wrapper around one) on the device of `states` [B,12] float32; `out` = a contiguous int32 [B] tensor to write
+    the actions into (e.g. the environment's bound action buffer).  Returns (actions int32 [B], probs or None)."""
+    net = policy.module if hasattr(policy, "module") else policy
+    x = states if (states.dtype == torch.float32 and states.is_contiguous()) else states.float().contiguous()
+    dev = x.device
+    if dev.type != "cuda":
+        raise _cabi.UavSimError("fused_policy_sample needs CUDA tensors (no CPU fallback)")
+    B, H, A = x.shape[0], net.fc1.out_features, net.fc2.out_features
+    w = _cabi.UavSimPolicyWeights()
+    w.state_dim, w.hidden, w.n_actions = x.shape[1], H, A
+    params = [net.fc1.weight, net.fc1.bias, net.fc2.weight, net.fc2.bias]
+    params = [p.detach() if p.is_contiguous() else p.detach().contiguous() for p in params]
+    w.w1, w.b1, w.w2, w.b2 = (p.data_ptr() for p in params)
+    if out is not None:
+        assert out.dtype == torch.int32 and out.is_contiguous() and out.numel() == B and out.device == dev
+    actions = out if out is not None else torch.empty(B, dtype=torch.int32, device=dev)
+    probs = torch.empty(B, A, dtype=torch.float32, device=dev) if want_probs else None
+    lib = _cabi.load()
+    with torch.cuda.device(dev):
+        _cabi.check(lib.uavsim_policy_sample(C.c_void_p(x.data_ptr()), B, C.byref(w), C.c_uint64(seed), C.c_uint64(counter),
+                                             C.c_void_p(actions.data_ptr()),
+                                             C.c_void_p(probs.data_ptr()) if probs is not None else None,
+                                             dev.index or 0, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                    "uavsim_policy_sample")
+    return actions, probs
+
+
 class BatchedActorCritic:
     """Same constructor and update rule as the reference `ActorCritic` (src/models/actor_critic.py:116-179), but
     `take_actions` works on all agents of all environments at once and `update` takes device tensors."""
 
-    def __init__(self, state_dim, hidden_dim, action_dim, actor_lr, critic_lr, gamma, device, ddp=False):
+    def __init__(self, state_dim, hidden_dim, action_dim, actor_lr, critic_lr, gamma, device, ddp=False, seed=0,
+                 fused=True):
         self.actor = PolicyNet(state_dim, hidden_dim, action_dim).to(device)
         self.critic = ValueNet(state_dim, hidden_dim).to(device)
         if ddp:  # gradient all-reduce over NCCL when several ranks train one policy
@@ -52,10 +86,17 @@ class BatchedActorCritic:
         self.actor_optimizer = torch.optim.Adam(self.actor.parameters(), lr=actor_lr)
         self.critic_optimizer = torch.optim.Adam(self.critic.parameters(), lr=critic_lr)
         self.gamma, self.device = gamma, device
+        # rollout policy step: the fused kernel draws from Philox (seed; row, call number); fused=False is the stock
+        # torch forward + multinomial
+        self.fused = bool(fused) and torch.device(device).type == "cuda" and state_dim == 12 and action_dim <= 16
+        self.seed, self._calls = int(seed), 0
 
     @torch.no_grad()
-    def take_actions(self, states):
-        """states [B,12] float -> (actions [B] int32, probs [B,na])."""
+    def take_actions(self, states, out=None):
+        """states [B,12] float -> (actions [B] int32, probs [B,na] or None on the fused path)."""
+        if self.fused:
+            self._calls += 1
+            return fused_policy_sample(self.actor, states, self.seed, self._calls, out=out)
         probs = self.actor(states)
         actions = torch.multinomial(probs, 1).squeeze(1)  # Categorical(probs).sample()
         return actions.to(torch.int32), probs
@@ -89,8 +130,14 @@ def operate_epoch_batched(config, env, agent, pmi, num_steps, keep_transitions=T
     bufs = {"states": [], "actions": [], "rewards": [], "next_states": []} if keep_transitions else None
     for step in range(num_steps):
         config["step"] = step + 1
-        actions, _ = agent.take_actions(states)
-        obs, rew4, _ = env.step_device(config, pmi, actions.view(E, n))
+        if getattr(agent, "fused", False):  # the policy kernel writes straight into the environment's action buffer
+            actions, _ = agent.take_actions(states, out=env.actions.view(-1))
+            obs, rew4, _ = env.step_device(config, pmi)
+            if keep_transitions:
+                actions = actions.clone()
+        else:
+            actions, _ = agent.take_actions(states)
+            obs, rew4, _ = env.step_device(config, pmi, actions.view(E, n))
         next_states = obs.reshape(E * n, 12)
         if keep_transitions:
             bufs["states"].append(states)
