@@ -169,19 +169,26 @@ def run_reference_arm(args, rank, world):
     mode = {"MAAC": 0, "MAAC-G": 1, "MAAC-R": 2}[method]
     pmi = oracle_pmi_from_module(make_pmi(torch)) if method == "MAAC-R" else None
     orc = Oracle()
-    # bounded sample: enough envs to keep every thread busy, sized so K+W steps end within ~2 minutes
+    # bounded sample: enough envs to keep every thread busy; one probe step sizes it so that K+W steps take ~1.5 x --cpu-seconds
+    # (more environments per call when the steps are short, so thread start-up does not dominate; fewer when long)
     Es = max(threads * 8, 16)
-    st = {k: np.ascontiguousarray(v) for k, v in reset_reference(0, Es, n, m, 12, 2000, 2000).items()}
+    probe = {k: np.ascontiguousarray(v) for k, v in reset_reference(0, Es, n, m, 12, 2000, 2000).items()}
     rng = np.random.RandomState(0)
     acts = rng.randint(0, 12, size=(Es, n)).astype(np.int32)
+    orc.step_batch(P, mode, float(cfg["cooperative"]), pmi, probe, acts, nthreads=threads, want_tracker=False)  # page-in
     t0 = time.perf_counter()
-    orc.step_batch(P, mode, float(cfg["cooperative"]), pmi, st, acts, nthreads=threads, want_tracker=False)
-    one = max(time.perf_counter() - t0, 1e-5)
-    total = args.steps + args.warmup
-    while Es > threads and one * total > 120:
-        Es //= 2
-        one /= 2
-    st = {k: np.ascontiguousarray(v[:Es]) for k, v in st.items()}
+    orc.step_batch(P, mode, float(cfg["cooperative"]), pmi, probe, acts, nthreads=threads, want_tracker=False)
+    one = max(time.perf_counter() - t0, 1e-6)
+    total = max(args.steps + args.warmup, 1)
+    scale = 1.5 * args.cpu_seconds / (one * total)   # default --cpu-seconds 12 -> ~18 s of CPU work
+    if scale >= 2:
+        Es *= int(min(scale, 256))
+    else:
+        while Es > threads and one * total > 120:
+            Es //= 2
+            one /= 2
+    Es = min(Es, E)
+    st = {k: np.ascontiguousarray(v) for k, v in reset_reference(0, Es, n, m, 12, 2000, 2000).items()}
     for _ in range(args.warmup):
         orc.step_batch(P, mode, float(cfg["cooperative"]), pmi, st, rng.randint(0, 12, size=(Es, n)).astype(np.int32),
                        nthreads=threads, want_tracker=False)
