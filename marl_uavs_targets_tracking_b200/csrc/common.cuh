@@ -44,7 +44,7 @@ struct KParams {
   double inv_dp, inv_dc, inv_na, inv_tt_hi, inv_dup_span;  // reciprocals for fp32-bound outputs
   // fp32 prefilter: map centre, validity radius, guarded squared thresholds (thr^2 + fp32 error bound)
   double cx, cy, rmax;
-  float f_dp, f_dcmv;         // targets: dp; UAVs: dc + dt*v_max (a partner's old position bounded through its new one)
+  float f_dp, f_dcmv;         // targets: dp; UAVs: max(dc + dt*v_max, 2 dp) (old position bounded through the new one)
 };
 
 struct PmiDev {

@@ -319,7 +319,7 @@ __device__ __forceinline__ uint32_t pair_chunk(const KParams &P, const UavSimBuf
   if (far_env) {
     cn = co = low_bits(len);
   } else {
-    // ONE guarded threshold, dc + dt*v, for both lists: finer masks (exactly dc for moved partners, 2dp for the
+    // ONE guarded threshold, max(dc + dt*v, 2 dp), for both lists: finer masks (exactly dc for moved partners, 2dp for the
     // reward-only evaluations) saved fewer exact evaluations than their extra compare + select cost on every pair
     cn = co = prefilter(V.nposf() + jb / 2, len, xf, yf, P.f_dcmv);
   }

@@ -116,7 +116,13 @@ extern "C" int uavsim_create(const UavSimParams *p, int64_t n_envs, int64_t env_
   k.cx = p->x_max / 2; k.cy = p->y_max / 2;
   k.rmax = 32768.0;
   k.f_dp = prefilter_threshold(p->dp, k.rmax);
-  k.f_dcmv = prefilter_threshold(p->dc + fabs(k.dtv_u) * (1.0 + 1e-9), k.rmax);
+  {  // one radius for every UAV-UAV test of a step: communication at the partner's new position (dc) or at its old
+     // position, bounded through the new one (dc + dt*v), duplicate tracking (2 dp) and the neighbour set (dp).  With
+     // the shipped constants dc + dt*v = 520 dominates; a scenario with 2 dp > dc + dt*v needs the larger one.
+    double r_uav = p->dc + fabs(k.dtv_u) * (1.0 + 1e-9);
+    if (2.0 * p->dp > r_uav) r_uav = 2.0 * p->dp;
+    k.f_dcmv = prefilter_threshold(r_uav, k.rmax);
+  }
 
   // per action: dt * discrete_action(a) (src/agent/uav.py:73-81, :96) in the reference's evaluation order,
   // plus its cosine / sine for the angle-addition update of the observation heading terms

@@ -208,6 +208,49 @@ def test_unusual_actions_and_time_steps(oracle):
     env.close()
 
 
+@pytest.mark.parametrize("case", range(18))
+def test_random_scenarios_match_the_oracle(oracle, case):
+    """Scenario constants drawn at random (map size, speeds, time step, ranges incl. dp > dc, action count, reward
+    weights, swarm sizes 1..70): the exact squared thresholds, the prefilter guard bands and the run-time-size kernel
+    are exercised away from the shipped YAML values."""
+    from marl_uavs_targets_tracking_b200 import PMINetwork, default_config
+    rng = np.random.RandomState(1000 + case)
+    n, m = int(rng.randint(1, 71)), int(rng.randint(1, 71))
+    method = ("MAAC", "MAAC-G", "MAAC-R")[case % 3]
+    cfg = default_config(method, n, m)
+    side = float(rng.choice([300.0, 2000.0, 9000.0]))
+    cfg["environment"].update(x_max=side, y_max=side * float(rng.uniform(0.5, 1.5)), na=int(rng.randint(2, 17)))
+    cfg["uav"].update(v_max=float(rng.uniform(1, 60)), dt=float(rng.choice([0.25, 1.0, 2.0])), h_max=float(rng.uniform(2, 12)),
+                      dc=float(rng.uniform(0.05, 0.6) * side), dp=float(rng.uniform(0.02, 0.7) * side),
+                      alpha=float(rng.uniform(0, 1)), beta=float(rng.uniform(0, 1)), gamma=float(rng.uniform(0, 1)))
+    cfg["target"].update(v_max=float(rng.uniform(0.5, 30)))
+    cfg["cooperative"] = float(rng.uniform(0.05, 0.9)) if method != "MAAC" else 0.0
+    pmi = None
+    if method == "MAAC-R":
+        torch.manual_seed(case)
+        pmi = PMINetwork(hidden_dim=int(rng.choice([64, 128]))).eval()
+    E, T = 37, 25
+    e = cfg["environment"]
+    from marl_uavs_targets_tracking_b200 import BatchedEnvironment
+    env = BatchedEnvironment(n, m, e["x_max"], e["y_max"], e["na"], n_envs=E, device="cuda:0", track_counts=True, seed=case)
+    env.reset(cfg)
+    P = oracle_params_from_config(cfg, n, m)
+    opmi = oracle_pmi_from_module(pmi) if pmi is not None else None
+    st = {k: np.ascontiguousarray(v.cpu().numpy()) for k, v in env.get_state().items()}
+    wo = wr = 0.0
+    for t in range(T):
+        a = env.random_actions(5, t).cpu().numpy().copy()
+        obs, rew4, cov = env.step_device(cfg, pmi)
+        ref = oracle.step_batch(P, case % 3, float(cfg["cooperative"]), opmi, st, a, nthreads=8)
+        assert np.array_equal(cov.cpu().numpy(), ref["covered"]), (case, t)
+        assert np.array_equal(env.tracker_counts.cpu().numpy(), ref["tracker_cnt"]), (case, t)
+        wo = max(wo, max_scaled_err(obs.double().cpu().numpy(), ref["obs"]))
+        wr = max(wr, max_scaled_err(rew4.double().cpu().numpy(), ref["rew4"]))
+    print("case", case, n, m, method, "obs %.1e rew %.1e" % (wo, wr))
+    assert wo <= TOL_TIGHT and wr <= (TOL_PMI if method == "MAAC-R" else TOL_TIGHT)
+    env.close()
+
+
 def test_long_episode_64x64_does_not_stall():
     """A full 200-step episode at 64x64 with many environments (UAVs do reach the origin corner)."""
     from marl_uavs_targets_tracking_b200 import default_config
