@@ -195,3 +195,43 @@ def test_train_pmi_on_the_device_and_reward_refresh():
         env3.random_actions(9, t)
         _, rew_old, _ = env3.step_device(cfg, old.eval())
     assert (rew_old[0] - rew_new[0]).abs().max() > 1e-6
+
+
+@pytest.mark.parametrize("case", range(6))
+def test_device_replay_random_operation_sequences(case):
+    """Random capacities, alphas, batch sizes (larger than the buffer, larger than the capacity), repeated indices:
+    every add / sample / update_priorities call against the numpy oracle of the reference class."""
+    rng = np.random.RandomState(50 + case)
+    C = int(rng.choice([1, 7, 64, 1000, 4097, 20000]))
+    alpha, beta = float(rng.uniform(0.1, 1.0)), float(rng.uniform(0.1, 1.0))
+    buf, o = _buffer(C, alpha), ReplayOracle(C, alpha)
+    for op in range(14):
+        k = int(rng.choice([1, 3, C // 2 + 1, C, C + 5, 2 * C + 3]))
+        s, s2 = rng.randn(k, 12).astype(np.float32), rng.randn(k, 12).astype(np.float32)
+        a, r = rng.randint(0, 12, k).astype(np.int32), rng.randn(k).astype(np.float32)
+        buf.add({"states": _t(s), "actions": _t(a), "rewards": _t(r), "next_states": _t(s2)})
+        o.add(s, a, r, s2)  # the reference's one-by-one loop
+        assert (buf.pos, buf.size()) == (o.pos, o.n)
+        ex = buf.export()
+        assert np.array_equal(ex["priorities"].numpy(), o.priorities)
+        assert np.array_equal(ex["states"].numpy(), o.states[:o.n]) and np.array_equal(ex["actions"].numpy(), o.actions[:o.n])
+        b = int(rng.choice([1, 5, o.n, o.n + 9, 3 * C]))
+        u = rng.random_sample(min(b, o.n))
+        sample, idx, w = buf.sample(b, beta, uniforms=_t(u))
+        oi, ow, oprob = o.sample(b, u, beta)
+        gi = idx.cpu().numpy()
+        assert gi.shape == oi.shape
+        prob = buf.export()["probabilities"].numpy()
+        cdf = np.cumsum(prob.astype(np.float64))
+        cdf /= cdf[-1]
+        assert np.array_equal(gi, np.searchsorted(cdf, u, side="right"))          # exact given the device's probabilities
+        assert np.allclose(prob, oprob, rtol=1e-6, atol=0)
+        assert (gi != oi).mean() <= 0.02 and np.abs(gi - oi).max() <= 1
+        same = gi == oi
+        assert np.allclose(w.cpu().numpy()[same], ow[same], rtol=1e-5, atol=0)
+        assert np.array_equal(sample["next_states"].cpu().numpy(), o.next_states[gi])
+        newp = (np.abs(rng.randn(len(gi))) + 1e-3).astype(np.float32)
+        order = rng.permutation(len(gi))                                           # repeated indices in random order
+        buf.update_priorities(_t(gi[order]), _t(newp[order]))
+        o.update_priorities(gi[order], newp[order])
+        assert np.array_equal(buf.export()["priorities"].numpy(), o.priorities), (case, op)
