@@ -152,6 +152,48 @@ def test_origin_corner_in_the_warp_uniform_kernel(oracle):
     env.close()
 
 
+@pytest.mark.parametrize("case", range(6))
+def test_origin_corner_under_random_scenarios(oracle, case):
+    """The exact per-row path (UAVs inside the 4 m x 4 m origin corner, weight quirk of uav.py:162-186) with random
+    scenario constants, small maps (many entities near the corner) and the shape-specialised kernels."""
+    from marl_uavs_targets_tracking_b200 import BatchedEnvironment, default_config
+    rng = np.random.RandomState(300 + case)
+    n, m = [(64, 64), (10, 10), (7, 33), (40, 3), (100, 9), (64, 64)][case]
+    method = ("MAAC", "MAAC-G")[case % 2]
+    cfg = default_config(method, n, m)
+    side = float(rng.choice([40.0, 300.0, 2000.0]))
+    cfg["environment"].update(x_max=side, y_max=side, na=int(rng.randint(2, 13)))
+    cfg["uav"].update(v_max=float(rng.uniform(0.5, 8)), dt=float(rng.choice([0.5, 1.0])), dc=float(rng.uniform(0.1, 0.9) * side),
+                      dp=float(rng.uniform(0.05, 0.6) * side))
+    cfg["target"].update(v_max=float(rng.uniform(0.1, 3)))
+    cfg["cooperative"] = 0.4 if method == "MAAC-G" else 0.0
+    E = 9
+    e = cfg["environment"]
+    env = BatchedEnvironment(n, m, e["x_max"], e["y_max"], e["na"], n_envs=E, device="cuda:0", track_counts=True, seed=case)
+    env.reset(cfg)
+    st = env.get_state()
+    for env_i in range(E):
+        for _ in range(int(rng.randint(0, 4))):        # some environments keep no corner UAV
+            i = int(rng.randint(0, n))
+            st["ux"][env_i, i], st["uy"][env_i, i] = float(rng.uniform(-2.5, 2.5)), float(rng.uniform(-2.5, 2.5))
+        if rng.rand() < 0.5:                           # a target and a partner close to the corner
+            st["tx"][env_i, int(rng.randint(0, m))], st["ty"][env_i, int(rng.randint(0, m))] = float(rng.uniform(0, 5)), float(rng.uniform(0, 5))
+            j = int(rng.randint(0, n))
+            st["ux"][env_i, j], st["uy"][env_i, j] = float(rng.uniform(0, 6)), float(rng.uniform(0, 6))
+    env.set_state(cfg, *(st[k] for k in ("ux", "uy", "uh", "ua", "tx", "ty", "th")))
+    P = oracle_params_from_config(cfg, n, m)
+    host = {k: np.ascontiguousarray(v.cpu().numpy()) for k, v in env.get_state().items()}
+    for t in range(8):
+        a = env.random_actions(3, t).cpu().numpy().copy()
+        obs, rew4, cov = env.step_device(cfg, None)
+        ref = oracle.step_batch(P, case % 2, float(cfg["cooperative"]), None, host, a, nthreads=4)
+        assert np.array_equal(cov.cpu().numpy(), ref["covered"]), (case, t)
+        assert np.array_equal(env.tracker_counts.cpu().numpy(), ref["tracker_cnt"]), (case, t)
+        assert max_scaled_err(obs.double().cpu().numpy(), ref["obs"]) <= TOL_TIGHT, (case, t)
+        assert max_scaled_err(rew4.double().cpu().numpy(), ref["rew4"]) <= TOL_TIGHT, (case, t)
+    env.close()
+
+
 @pytest.mark.parametrize("n,m", [(64, 64), (10, 10), (20, 7)])
 def test_entities_beyond_the_prefilter_radius(oracle, n, m):
     """The fp32 prefilter is only proven within 32 768 m of the map centre; environments with an entity outside
