@@ -192,7 +192,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default=os.environ.get("UAVSIM_REFERENCE_SRC", "/root/reference/src"))
     ap.add_argument("--out", default=os.path.dirname(os.path.abspath(__file__)))
+    ap.add_argument("--only", default="", help="comma-separated case names (default: all)")
     args = ap.parse_args()
+    only = set(filter(None, args.only.split(",")))
+    global run_case
+    _run = run_case
+
+    def run_case(name, *a, **k):  # noqa: F811
+        if not only or name in only:
+            _run(name, *a, **k)
     sys.path.insert(0, args.ref)
     import torch
     torch.set_num_threads(1)
@@ -235,6 +243,16 @@ def main():
                uav__dt=0.5, uav__v_max=30, uav__h_max=4, uav__dc=300, uav__dp=120,
                uav__alpha=0.5, uav__beta=0.3, uav__gamma=0.2, target__v_max=8, target__h_max=5)
     run_case("odd_pmi_h64", args.out, mods, odd2, "pmi", 120, 22, pmi_hidden=64)
+    # perception range wider than the communication range: the duplicate-tracking radius 2*dp (uav.py:225) exceeds
+    # dc + dt*v, and every UAV sees most targets
+    wide = cfg(12, 9, 0.6, environment__x_max=1200, environment__y_max=1000, environment__na=10,
+               uav__dt=1, uav__v_max=25, uav__h_max=5, uav__dc=150, uav__dp=400,
+               uav__alpha=0.3, uav__beta=0.3, uav__gamma=0.4, target__v_max=6, target__h_max=6)
+    run_case("wide_dp_mean", args.out, mods, wide, "mean", 100, 51)
+    wide2 = cfg(12, 9, 0.6, environment__x_max=1200, environment__y_max=1000, environment__na=10,
+                uav__dt=1, uav__v_max=25, uav__h_max=5, uav__dc=150, uav__dp=400,
+                uav__alpha=0.3, uav__beta=0.3, uav__gamma=0.4, target__v_max=6, target__h_max=6)
+    run_case("wide_dp_pmi", args.out, mods, wide2, "pmi", 60, 52)
     # weight quirk: UAVs flying through the origin
     T = 12
     na = 12

@@ -4,7 +4,8 @@ tests/golden/*.npz were produced by tests/golden/make_golden.py, which imports a
 unmodified reference (environment.py / agent/uav.py / agent/target.py / models/PMINet.py) in the
 build container.  Integer outputs must match bit for bit; positions, headings and observations are
 required to be bit-equal too (same libm, same evaluation order); rewards within 1e-12 (MAAC / MAAC-G)
-or 5e-8 (MAAC-R: fp32 MLP summation order differs from torch's GEMV).
+or 1.7e-7 x cooperative (MAAC-R: the fp32 MLP's summation order differs from torch's GEMV, a float32-epsilon effect on
+the softmax weights that enters the reward scaled by `cooperative`; 5e-8 at the shipped 0.3).
 """
 import numpy as np
 import pytest
@@ -24,7 +25,7 @@ def test_oracle_matches_reference(oracle, name):
     st = {k: np.array(g[k + "0"]) for k in STATE + ("ua",)}
     assert np.array_equal(oracle.initial_obs(P, st["ux"], st["uy"], st["ua"]), g["obs0"])
     T = g["actions"].shape[0]
-    rtol = 5e-8 if mode == 2 else 1e-12
+    rtol = max(5e-8, 1.7e-7 * coop) if mode == 2 else 1e-12
     for t in range(T):
         out = oracle.step(P, mode, coop, pmi, st, g["actions"][t])
         for k in STATE:
