@@ -491,6 +491,20 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
     const int64_t e0 = env_begin + grp * epb;
     const int ne = (int)min((int64_t)epb, env_begin + env_count - e0);
     if (tid < epb) { S.far[tid] = 0; S.cov[tid] = 0; }  // (their readers of the previous iteration have passed a barrier)
+    if (!WARP_ENV) {
+      // Small-swarm instances are bound by global-load latency, not by issue slots (10x10: long-scoreboard stalls
+      // dominate): pull the state of this CTA's NEXT group of environments into L2 while this one is computed, one
+      // prefetch per 128-byte line.  (The 64x64 instance is issue-bound; there the extra instructions cost more than
+      // the latency they hide.)
+      const int64_t grp_n = grp + gridDim.x;
+      if (grp_n < ngroups) {
+        const int64_t e0n = env_begin + grp_n * epb;
+        auto pf = [](const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); };
+        for (int q = tid * 16; q < epb * n; q += NT * 16) { pf(B.ux + e0n * n + q); pf(B.uy + e0n * n + q); pf(B.uh + e0n * n + q); }
+        for (int q = tid * 32; q < epb * n; q += NT * 32) { pf(B.ua + e0n * n + q); pf(B.actions + e0n * n + q); }
+        for (int q = tid * 16; q < epb * m; q += NT * 16) { pf(B.tx + e0n * m + q); pf(B.ty + e0n * m + q); pf(B.th + e0n * m + q); }
+      }
+    }
     __syncthreads();                // previous iteration's readers are done; dth table visible
 
     // ---- phase 0a: targets (src/agent/target.py:27-60) ----
