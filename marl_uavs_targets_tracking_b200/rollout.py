@@ -103,13 +103,15 @@ class BatchedActorCritic:
 
     def update(self, states, actions, rewards, next_states):
         """One-step TD actor-critic update on [B,...] device tensors (src/models/actor_critic.py:150-179)."""
-        td_target = rewards + self.gamma * self.critic(next_states)
-        td_delta = td_target - self.critic(states)
+        with torch.no_grad():  # the reference detaches td_target in both losses (actor_critic.py:171-173)
+            td_target = rewards + self.gamma * self.critic(next_states)
+        v = self.critic(states)  # evaluated once; the reference's two evaluations give the same value
+        td_delta = td_target - v
         log_probs = torch.log(self.actor(states).gather(1, actions.long().view(-1, 1)))
         # The reference multiplies log_probs [B,1] by td_delta [B]: that broadcasts to a [B,B] outer product whose mean
         # is mean(-log_probs) * mean(td_delta) (src/models/actor_critic.py:171).  Same value and gradient, O(B) memory.
         actor_loss = torch.mean(-log_probs) * torch.mean(td_delta.detach())
-        critic_loss = F.mse_loss(self.critic(states), td_target.detach())
+        critic_loss = F.mse_loss(v, td_target)
         self.actor_optimizer.zero_grad()
         self.critic_optimizer.zero_grad()
         actor_loss.backward()

@@ -3,6 +3,7 @@
 
 * `learner_pmi_train.npz`  -- `PMINetwork.train_pmi` (src/models/PMINet.py:74-100): initial weights, training data,
   the index draws, the returned average loss and the weights / BatchNorm statistics after the call.
+* `learner_ac_update.npz` -- `ActorCritic.update` (src/models/actor_critic.py:150-179): two consecutive updates.
 * `learner_per.npz`        -- `PrioritizedReplayBuffer` (src/train.py:73-139): a recorded sequence of add / sample /
   update_priorities calls with the priorities after every call, and for every sample call the probabilities, the
   indices numpy drew, the uniforms that produce them under numpy's own inverse-CDF rule and the importance weights.
@@ -39,8 +40,43 @@ def import_reference(ref):
             m.SummaryWriter = object
             sys.modules[name] = m
     from models.PMINet import PMINetwork
+    from models.actor_critic import ActorCritic
     import train as ref_train
-    return PMINetwork, ref_train.PrioritizedReplayBuffer
+    return PMINetwork, ref_train.PrioritizedReplayBuffer, ActorCritic
+
+
+def actor_critic_case(ActorCritic):
+    """ActorCritic.update (src/models/actor_critic.py:150-179): weights before, a batch, losses, TD errors, weights after
+    two consecutive updates (Adam state carries over)."""
+    torch.manual_seed(21)
+    torch.set_num_threads(1)
+    B, H, A = 96, 24, 12
+    ac = ActorCritic(12, H, A, 1e-3, 2e-3, 0.95, torch.device("cpu"))
+    out = {"hidden": H, "n_actions": A, "actor_lr": 1e-3, "critic_lr": 2e-3, "gamma": 0.95}
+    for k, v in ac.actor.state_dict().items():
+        out["init.actor." + k] = v.detach().clone().numpy()
+    for k, v in ac.critic.state_dict().items():
+        out["init.critic." + k] = v.detach().clone().numpy()
+    rng = np.random.RandomState(4)
+    for step in range(2):
+        batch = {"states": [rng.randn(12).astype(np.float32) for _ in range(B)],
+                 "actions": [int(a) for a in rng.randint(0, A, B)],
+                 "rewards": [float(r) for r in rng.uniform(-1, 1, B)],
+                 "next_states": [rng.randn(12).astype(np.float32) for _ in range(B)]}
+        a_loss, c_loss, td = ac.update(batch)
+        out["step%d.states" % step] = np.array(batch["states"])
+        out["step%d.actions" % step] = np.array(batch["actions"], np.int64)
+        out["step%d.rewards" % step] = np.array(batch["rewards"], np.float32)
+        out["step%d.next_states" % step] = np.array(batch["next_states"])
+        out["step%d.actor_loss" % step] = np.float64(a_loss.item())
+        out["step%d.critic_loss" % step] = np.float64(c_loss.item())
+        out["step%d.td" % step] = td.detach().numpy()
+    for k, v in ac.actor.state_dict().items():
+        out["final.actor." + k] = v.detach().numpy()
+    for k, v in ac.critic.state_dict().items():
+        out["final.critic." + k] = v.detach().numpy()
+    np.savez_compressed(os.path.join(HERE, "learner_ac_update.npz"), **out)
+    print("learner_ac_update: losses", out["step1.actor_loss"], out["step1.critic_loss"])
 
 
 def pmi_train_case(PMINetwork):
@@ -128,7 +164,12 @@ def per_case(PER):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference/src")
+    ap.add_argument("--only", default="")
     args = ap.parse_args()
-    PMINetwork, PER = import_reference(args.ref)
-    pmi_train_case(PMINetwork)
-    per_case(PER)
+    PMINetwork, PER, ActorCritic = import_reference(args.ref)
+    if args.only in ("", "pmi"):
+        pmi_train_case(PMINetwork)
+    if args.only in ("", "per"):
+        per_case(PER)
+    if args.only in ("", "ac"):
+        actor_critic_case(ActorCritic)

@@ -59,3 +59,27 @@ def test_train_pmi_matches_the_reference_on_cpu():
         other.load(os.path.join(d, "pmi", "pmi_weights_3.pth"))
         for k, v in other.state_dict().items():
             assert torch.equal(v, net.state_dict()[k]), k
+
+
+def test_actor_critic_update_matches_the_reference_on_cpu():
+    """BatchedActorCritic.update == ActorCritic.update (src/models/actor_critic.py:150-179) on a recorded pair of
+    consecutive updates: losses, TD errors and every weight after Adam.  (The reference multiplies log_probs [B,1] by
+    td_delta [B]: the mean over the [B,B] outer product is mean(-log_probs) * mean(td_delta), which is what the
+    batched class evaluates in O(B).)"""
+    from marl_uavs_targets_tracking_b200.rollout import BatchedActorCritic
+    g = load_golden("learner_ac_update")
+    torch.set_num_threads(1)
+    ac = BatchedActorCritic(12, int(g["hidden"]), int(g["n_actions"]), float(g["actor_lr"]), float(g["critic_lr"]),
+                            float(g["gamma"]), torch.device("cpu"))
+    ac.actor.load_state_dict({k[len("init.actor."):]: torch.tensor(np.array(g[k])) for k in g.files if k.startswith("init.actor.")})
+    ac.critic.load_state_dict({k[len("init.critic."):]: torch.tensor(np.array(g[k])) for k in g.files if k.startswith("init.critic.")})
+    for step in range(2):
+        t = "step%d." % step
+        a_loss, c_loss, td = ac.update(torch.tensor(g[t + "states"]), torch.tensor(g[t + "actions"]),
+                                       torch.tensor(g[t + "rewards"]), torch.tensor(g[t + "next_states"]))
+        assert abs(float(a_loss) - float(g[t + "actor_loss"])) <= 2e-6 * max(1.0, abs(float(g[t + "actor_loss"])))
+        assert abs(float(c_loss) - float(g[t + "critic_loss"])) <= 2e-6 * max(1.0, abs(float(g[t + "critic_loss"])))
+        assert np.allclose(td.numpy(), g[t + "td"], rtol=1e-5, atol=1e-6)
+    for name, net in (("actor", ac.actor), ("critic", ac.critic)):
+        for k, v in net.state_dict().items():
+            assert np.allclose(v.numpy(), g["final.%s.%s" % (name, k)], rtol=1e-4, atol=2e-6), (name, k)
