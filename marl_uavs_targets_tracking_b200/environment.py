@@ -274,6 +274,16 @@ class BatchedEnvironment:
         """The bound int32 [E,n] action buffer the next step_device(config, pmi) call reads."""
         return self._actions
 
+    def bind_obs(self, obs):
+        """Point the kernel at another resident float32 [E,n,12] observation buffer (no copy): the next step writes its
+        observations there and `get_states()` returns it.  A rollout binds slot t+1 of a [T+1,E,n,12] trajectory
+        tensor before step t, so states and next_states of every transition are views of one tensor and nothing is
+        copied per step.  The caller keeps the tensor alive while it is bound."""
+        assert obs.dtype == torch.float32 and obs.is_contiguous() and obs.numel() == self.n_envs * self.n_uav * 12
+        assert obs.device == self._obs.device
+        self._obs = obs.view(self.n_envs, self.n_uav, 12)
+        self._bind()
+
     def bind_actions(self, actions):
         """Point the kernel at another resident int32 [E,n] action tensor (no copy)."""
         assert actions.dtype == torch.int32 and actions.is_contiguous() and actions.numel() == self.n_envs * self.n_uav

@@ -126,29 +126,52 @@ def operate_epoch_batched(config, env, agent, pmi, num_steps, keep_transitions=T
 
     Returns (transitions, summary): transitions = dict of device tensors states [T*E*n,12], actions [T*E*n],
     rewards [T*E*n], next_states [T*E*n,12] (None if keep_transitions is False); summary = the six scalars the
-    reference logs per episode, averaged over every environment of every rank."""
+    reference logs per episode, averaged over every environment of every rank.
+
+    With keep_transitions the observations of the whole episode live in ONE [T+1,E,n,12] tensor: the environment's
+    observation buffer is re-bound to slot t+1 before step t, so `states` and `next_states` are overlapping views of it
+    and no observation is copied; the fused policy kernel writes the actions into slot t of the action trajectory,
+    which is bound as the environment's action buffer."""
     E, n = env.n_envs, env.n_uav
-    states = env.get_states().reshape(E * n, 12).clone()
-    bufs = {"states": [], "actions": [], "rewards": [], "next_states": []} if keep_transitions else None
-    for step in range(num_steps):
-        config["step"] = step + 1
-        if getattr(agent, "fused", False):  # the policy kernel writes straight into the environment's action buffer
-            actions, _ = agent.take_actions(states, out=env.actions.view(-1))
-            obs, rew4, _ = env.step_device(config, pmi)
-            if keep_transitions:
-                actions = actions.clone()
-        else:
-            actions, _ = agent.take_actions(states)
-            obs, rew4, _ = env.step_device(config, pmi, actions.view(E, n))
-        next_states = obs.reshape(E * n, 12)
-        if keep_transitions:
-            bufs["states"].append(states)
-            bufs["actions"].append(actions)
-            bufs["rewards"].append(rew4[0].reshape(E * n).clone())
-            bufs["next_states"].append(next_states.clone())
-        states = next_states.clone()
+    dev = env.device
+    fused = bool(getattr(agent, "fused", False))
+    if keep_transitions:
+        home_obs, home_act = env._obs, env.actions
+        traj = torch.empty((num_steps + 1, E, n, 12), dtype=torch.float32, device=dev)
+        acts = torch.empty((num_steps, E, n), dtype=torch.int32, device=dev)
+        rews = torch.empty((num_steps, E * n), dtype=torch.float32, device=dev)
+        traj[0].copy_(env._obs)
+        try:
+            for step in range(num_steps):
+                config["step"] = step + 1
+                env.bind_obs(traj[step + 1])
+                env.bind_actions(acts[step])
+                states = traj[step].view(E * n, 12)
+                if fused:
+                    agent.take_actions(states, out=acts[step].view(-1))
+                else:
+                    a, _ = agent.take_actions(states)
+                    acts[step].view(-1).copy_(a)
+                _, rew4, _ = env.step_device(config, pmi)
+                rews[step].copy_(rew4[0].reshape(E * n))
+        finally:
+            home_obs.copy_(traj[num_steps])
+            env.bind_obs(home_obs)
+            env.bind_actions(home_act)
+        transitions = {"states": traj[:-1].reshape(num_steps * E * n, 12), "actions": acts.reshape(-1),
+                       "rewards": rews.reshape(-1), "next_states": traj[1:].reshape(num_steps * E * n, 12)}
+    else:
+        for step in range(num_steps):
+            config["step"] = step + 1
+            states = env._obs.view(E * n, 12)
+            if fused:
+                agent.take_actions(states, out=env.actions.view(-1))
+                env.step_device(config, pmi)
+            else:
+                a, _ = agent.take_actions(states)
+                env.step_device(config, pmi, a.view(E, n))
+        transitions = None
     stats = reduce_episode_stats(env.episode_stats(), device=env.device)
-    transitions = {k: torch.cat(v) for k, v in bufs.items()} if keep_transitions else None
     return transitions, episode_summary(stats, n)
 
 

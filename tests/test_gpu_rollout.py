@@ -21,6 +21,14 @@ def test_batched_rollout_and_update():
     assert torch.equal(tr["next_states"][:E * 10], tr["states"][E * 10:2 * E * 10])
     # the summary equals the mean of the collected rewards (src/train.py:187)
     assert abs(summary["return"] - float(tr["rewards"].double().mean())) < 1e-6
+    # the environment's own buffers are bound again and hold the last observation; stepping on works
+    assert torch.equal(env.get_states().reshape(-1, 12), tr["next_states"][-E * 10:])
+    assert env.get_states().data_ptr() != tr["next_states"].data_ptr()
+    env.random_actions(3, 0)
+    o_after, _, _ = env.step_device(cfg, None)
+    assert o_after.data_ptr() == env.get_states().data_ptr() and not torch.equal(o_after.reshape(-1, 12), tr["next_states"][-E * 10:])
+    # states / next_states are overlapping views of one trajectory tensor (no per-step copies)
+    assert tr["next_states"].data_ptr() == tr["states"].data_ptr() + E * 10 * 12 * 4
     assert 0 <= summary["average_covered_targets"] <= 10
     before = [p.detach().clone() for p in agent.actor.parameters()]
     a_loss, c_loss, td = agent.update(tr["states"], tr["actions"], tr["rewards"], tr["next_states"])
@@ -93,3 +101,34 @@ def test_fused_policy_kernel_matches_torch_forward_and_draws_from_it(hidden, na,
         keep = e > 5
         chi2 = (((cnt - e) ** 2 / np.maximum(e, 1e-30))[keep]).sum()
         assert chi2 < 60, (chi2, cnt, e)
+
+
+def test_rollout_paths_agree():
+    """keep_transitions on/off and the stock torch policy step drive the same environment dynamics: with the fused
+    policy (Philox draws keyed by call number) the two modes visit identical states."""
+    from marl_uavs_targets_tracking_b200 import BatchedEnvironment, default_config
+    from marl_uavs_targets_tracking_b200.rollout import BatchedActorCritic, operate_epoch_batched
+    cfg = default_config("MAAC-G", 10, 10)
+    E, T = 200, 15
+    dev = torch.device("cuda:0")
+    finals = []
+    for keep in (True, False):
+        env = BatchedEnvironment(10, 10, 2000, 2000, 12, n_envs=E, device=dev, seed=4)
+        env.reset(cfg)
+        torch.manual_seed(0)
+        agent = BatchedActorCritic(12, 64, 12, 1e-3, 1e-3, 0.95, dev, seed=7)
+        tr, summary = operate_epoch_batched(cfg, env, agent, None, T, keep_transitions=keep)
+        finals.append((env.get_states().clone(), {k: v.clone() for k, v in env.get_state().items()}, summary))
+        assert (tr is None) == (not keep)
+        env.close()
+    assert torch.equal(finals[0][0], finals[1][0])
+    assert all(torch.equal(finals[0][1][k], finals[1][1][k]) for k in finals[0][1])
+    assert finals[0][2] == finals[1][2]
+    # stock torch policy step (multinomial): same structure, valid actions
+    env = BatchedEnvironment(10, 10, 2000, 2000, 12, n_envs=E, device=dev, seed=4)
+    env.reset(cfg)
+    agent = BatchedActorCritic(12, 64, 12, 1e-3, 1e-3, 0.95, dev, fused=False)
+    tr, _ = operate_epoch_batched(cfg, env, agent, None, T)
+    assert tr["actions"].dtype == torch.int32 and 0 <= int(tr["actions"].min()) and int(tr["actions"].max()) < 12
+    assert torch.equal(tr["next_states"][:E * 10], tr["states"][E * 10:2 * E * 10])
+    env.close()
