@@ -4,11 +4,14 @@
 // `.item()` sync (src/models/actor_critic.py:138-148, src/train.py:160-176).  With the environment resident on the GPU
 // the policy step of a rollout is `probs = softmax(fc2(relu(fc1(obs))))` over all E*n rows followed by one categorical
 // draw per row (src/models/actor_critic.py:85-99): six small library kernels in stock PyTorch, which at 10x10 cost
-// twice the environment step.  Here it is ONE launch: a thread owns four rows, packed two by two into the halves of
-// Blackwell's f32x2 instructions, so every weight fetched from shared memory (broadcast) serves four rows; the hidden
-// activation is never materialised (each hidden unit is consumed by the logit accumulators as soon as it is
-// computed); softmax, inverse-CDF draw (Philox4x32-10 keyed (seed; row, counter)) and the optional probability
-// output happen in registers.  fp32 throughout, like the torch module.
+// twice the environment step.  Here it is ONE launch: a thread owns four rows; the two halves of Blackwell's f32x2
+// instructions carry two HIDDEN UNITS (j, j+1) of one row, so the weights arrive from shared memory already paired
+// (one broadcast LDS.128 = the pair's fc1 weights for two inputs, or its fc2 weights for two actions) and serve the
+// thread's four rows, while the row's inputs enter as scalar-broadcast operands -- no register shuffling in front of
+// the FFMA2s.  The hidden activation is never materialised: a unit pair is consumed by the logit accumulators (kept
+// as even-unit / odd-unit partial sums) as soon as it is computed; softmax, inverse-CDF draw (Philox4x32-10 keyed
+// (seed; row, counter)) and the optional probability output happen in registers.  fp32 throughout, like the torch
+// module (the summation order differs: 2e-6 on the probabilities).
 #pragma once
 #include "common.cuh"
 #include "philox.cuh"
@@ -35,70 +38,63 @@ __device__ __forceinline__ uint64_t pol_fma2(uint64_t a, uint64_t b, uint64_t c)
 __device__ __forceinline__ float pol_lo(uint64_t v) { return __uint_as_float((uint32_t)v); }
 __device__ __forceinline__ float pol_hi(uint64_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
 
-// shared memory: per hidden unit j a record of 32 floats {w1[j][0..11], b1[j], 0,0,0, w2[0..A-1][j], 0..} (128-bit loads)
+// shared memory: per hidden-unit pair (j, j+1) a record of 64 floats:
+//   [ 0..23]  {w1[j][k], w1[j+1][k]} for k = 0..11        [24..25] {b1[j], b1[j+1]}   [26..31] 0
+//   [32..63]  {w2[a][j], w2[a][j+1]} for a = 0..AP-1 (0 beyond the action count)
 // AP = number of actions rounded up to a multiple of 4; the padding logits are -inf (probability 0)
 template <int AP>
 __global__ void __launch_bounds__(POLICY_NT)
 uavsim_policy_kernel(const float *__restrict__ obs, int64_t rows, const PolicyDev W, uint64_t seed, uint64_t counter,
                      int32_t *__restrict__ actions, float *__restrict__ probs) {
   extern __shared__ __align__(16) float s_w[];
-  const int H = W.H, A = W.A;
-  for (int k = threadIdx.x; k < H * 32; k += POLICY_NT) {
-    const int j = k >> 5, e = k & 31;
+  const int H = W.H, A = W.A, HP = (H + 1) / 2;  // unit pairs (an odd H gets a zero unit: relu(0) * 0 adds nothing)
+  for (int k = threadIdx.x; k < HP * 64; k += POLICY_NT) {
+    const int jp = k >> 6, e = k & 63, j = 2 * jp + (e & 1);
     float v = 0.f;
-    if (e < POLICY_IN) v = W.w1[j * POLICY_IN + e];
-    else if (e == POLICY_IN) v = W.b1[j];
-    else if (e >= 16 && e < 16 + A) v = W.w2[(e - 16) * H + j];
+    if (j < H) {
+      if (e < 24) v = W.w1[j * POLICY_IN + (e >> 1)];
+      else if (e < 26) v = W.b1[j];
+      else if (e >= 32 && ((e - 32) >> 1) < A) v = W.w2[((e - 32) >> 1) * H + j];
+    }
     s_w[k] = v;
   }
   __syncthreads();
 
   const int64_t stride = (int64_t)gridDim.x * POLICY_NT * POLICY_ROWS;
   for (int64_t r0 = ((int64_t)blockIdx.x * POLICY_NT + threadIdx.x) * POLICY_ROWS; r0 < rows; r0 += stride) {
-    // rows r0 .. r0+3 (clamped reads; stores are guarded): x01[k] = {row0[k], row1[k]}, x23[k] = {row2[k], row3[k]}
-    uint64_t x01[POLICY_IN], x23[POLICY_IN];
-    {
-      const float4 *p[POLICY_ROWS];
+    float x[POLICY_ROWS][POLICY_IN];  // rows r0 .. r0+3 (clamped reads; stores are guarded)
 #pragma unroll
-      for (int q = 0; q < POLICY_ROWS; q++) p[q] = reinterpret_cast<const float4 *>(obs + min(r0 + q, rows - 1) * POLICY_IN);
+    for (int q = 0; q < POLICY_ROWS; q++) {
+      const float4 *p = reinterpret_cast<const float4 *>(obs + min(r0 + q, rows - 1) * POLICY_IN);
 #pragma unroll
       for (int v = 0; v < POLICY_IN / 4; v++) {
-        const float4 a = p[0][v], b = p[1][v], c = p[2][v], d = p[3][v];
-        x01[4 * v + 0] = pol_pack2(a.x, b.x); x01[4 * v + 1] = pol_pack2(a.y, b.y);
-        x01[4 * v + 2] = pol_pack2(a.z, b.z); x01[4 * v + 3] = pol_pack2(a.w, b.w);
-        x23[4 * v + 0] = pol_pack2(c.x, d.x); x23[4 * v + 1] = pol_pack2(c.y, d.y);
-        x23[4 * v + 2] = pol_pack2(c.z, d.z); x23[4 * v + 3] = pol_pack2(c.w, d.w);
+        const float4 t = p[v];
+        x[q][4 * v] = t.x; x[q][4 * v + 1] = t.y; x[q][4 * v + 2] = t.z; x[q][4 * v + 3] = t.w;
       }
     }
-    uint64_t l01[AP], l23[AP];
+    uint64_t lg2[POLICY_ROWS][AP];  // logit partial sums {over even units, over odd units}
 #pragma unroll
-    for (int a = 0; a < AP; a++) { const float b = a < A ? W.b2[a] : -INFINITY; l01[a] = pol_pack2(b, b); l23[a] = l01[a]; }
+    for (int q = 0; q < POLICY_ROWS; q++)
+#pragma unroll
+      for (int a = 0; a < AP; a++) lg2[q][a] = 0ull;
 
-#pragma unroll 2
-    for (int j = 0; j < H; j++) {
-      const float4 *wj = reinterpret_cast<const float4 *>(s_w + j * 32);
-      const float4 wa = wj[0], wb = wj[1], wc = wj[2], wd = wj[3];  // w1[j][0..11], {b1[j], 0, 0, 0}
-      const float w1j[POLICY_IN] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x, wc.y, wc.z, wc.w};
-      uint64_t h01 = pol_pack2(wd.x, wd.x), h23 = h01;
+#pragma unroll 1
+    for (int jp = 0; jp < HP; jp++) {
+      const ulonglong2 *wj = reinterpret_cast<const ulonglong2 *>(s_w + jp * 64);
+      uint64_t w1p[POLICY_IN], w2p[AP];
 #pragma unroll
-      for (int k = 0; k < POLICY_IN; k++) {
-        const uint64_t w = pol_pack2(w1j[k], w1j[k]);
-        h01 = pol_fma2(w, x01[k], h01);
-        h23 = pol_fma2(w, x23[k], h23);
-      }
-      h01 = pol_pack2(fmaxf(pol_lo(h01), 0.f), fmaxf(pol_hi(h01), 0.f));  // ReLU
-      h23 = pol_pack2(fmaxf(pol_lo(h23), 0.f), fmaxf(pol_hi(h23), 0.f));
-      float w2j[AP];
+      for (int v = 0; v < POLICY_IN / 2; v++) { const ulonglong2 t = wj[v]; w1p[2 * v] = t.x; w1p[2 * v + 1] = t.y; }
+      const uint64_t bp = wj[6].x;
 #pragma unroll
-      for (int v = 0; v < AP / 4; v++) {
-        const float4 t = wj[4 + v];
-        w2j[4 * v] = t.x; w2j[4 * v + 1] = t.y; w2j[4 * v + 2] = t.z; w2j[4 * v + 3] = t.w;
-      }
+      for (int v = 0; v < AP / 2; v++) { const ulonglong2 t = wj[8 + v]; w2p[2 * v] = t.x; w2p[2 * v + 1] = t.y; }
 #pragma unroll
-      for (int a = 0; a < AP; a++) {
-        const uint64_t w = pol_pack2(w2j[a], w2j[a]);
-        l01[a] = pol_fma2(w, h01, l01[a]);
-        l23[a] = pol_fma2(w, h23, l23[a]);
+      for (int q = 0; q < POLICY_ROWS; q++) {
+        uint64_t h = bp;
+#pragma unroll
+        for (int k = 0; k < POLICY_IN; k++) h = pol_fma2(w1p[k], pol_pack2(x[q][k], x[q][k]), h);
+        h = pol_pack2(fmaxf(pol_lo(h), 0.f), fmaxf(pol_hi(h), 0.f));  // ReLU of units j, j+1
+#pragma unroll
+        for (int a = 0; a < AP; a++) lg2[q][a] = pol_fma2(w2p[a], h, lg2[q][a]);
       }
     }
 
@@ -109,10 +105,7 @@ uavsim_policy_kernel(const float *__restrict__ obs, int64_t rows, const PolicyDe
       if (r >= rows) break;
       float lg[AP];
 #pragma unroll
-      for (int a = 0; a < AP; a++) {
-        const uint64_t v = (q < 2) ? l01[a] : l23[a];
-        lg[a] = (q & 1) ? pol_hi(v) : pol_lo(v);
-      }
+      for (int a = 0; a < AP; a++) lg[a] = a < A ? (pol_lo(lg2[q][a]) + pol_hi(lg2[q][a])) + W.b2[a] : -INFINITY;
       float mx = lg[0];
 #pragma unroll
       for (int a = 1; a < AP; a++) mx = fmaxf(mx, lg[a]);
@@ -142,14 +135,19 @@ uavsim_policy_kernel(const float *__restrict__ obs, int64_t rows, const PolicyDe
 template <int AP>
 static int policy_launch(const float *obs, int64_t rows, const PolicyDev &W, uint64_t seed, uint64_t counter,
                          int32_t *actions, float *probs, int device, cudaStream_t st) {
-  const size_t smem = (size_t)W.H * 32 * sizeof(float);
+  const size_t smem = (size_t)((W.H + 1) / 2) * 64 * sizeof(float);
   int rc = raise_dynamic_smem((const void *)uavsim_policy_kernel<AP>, device, smem);
   if (rc) return rc;
-  int sms = 148;
+  int sms = 148, occ = 1;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  int64_t blocks = (rows + (int64_t)POLICY_NT * POLICY_ROWS - 1) / ((int64_t)POLICY_NT * POLICY_ROWS);
-  const int64_t cap = (int64_t)sms * 8;
-  if (blocks > cap) blocks = cap;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, uavsim_policy_kernel<AP>, POLICY_NT, smem);
+  if (occ < 1) occ = 1;
+  // persistent, balanced grid: every CTA stages the weights once and runs the same number of 512-row iterations
+  // (a grid of "one CTA per iteration" pays the staging per iteration and ends in a mostly idle last wave)
+  const int64_t iters = (rows + (int64_t)POLICY_NT * POLICY_ROWS - 1) / ((int64_t)POLICY_NT * POLICY_ROWS);
+  const int64_t resident = (int64_t)sms * occ;
+  const int64_t per_cta = (iters + resident - 1) / resident;
+  int64_t blocks = (iters + per_cta - 1) / (per_cta > 0 ? per_cta : 1);
   if (blocks < 1) blocks = 1;
   uavsim_policy_kernel<AP><<<(int)blocks, POLICY_NT, smem, st>>>(obs, rows, W, seed, counter, actions, probs);
   CUDA_TRY(cudaGetLastError());
