@@ -61,6 +61,7 @@ SYMBOLS = {
     "uavsim_set_reward_weights": (C.c_int, [_H, C.c_double, C.c_double, C.c_double]),
     "uavsim_set_pmi_weights": (C.c_int, [_H, C.POINTER(UavSimPmiWeights), C.c_void_p]),
     "uavsim_set_pmi_path": (C.c_int, [_H, C.c_int]),
+    "uavsim_set_step_path": (C.c_int, [_H, C.c_int]),
     "uavsim_episode_stats": (C.c_int, [_H, C.POINTER(C.c_double), C.c_void_p]),
     "uavsim_launch_count": (C.c_int64, [_H]),
     "uavsim_step_count": (C.c_int64, [_H]),

@@ -27,6 +27,10 @@ static thread_local char g_err[512] = "";
 // ------------------------------------------------------------------------------------------------
 // kernel-side parameter block
 // ------------------------------------------------------------------------------------------------
+struct GuardK {
+  float t2_up, t2_dn, c1, c0;
+};
+
 struct KParams {
   int n, m, na, num_steps;
   int64_t E;                  // environments of this handle (plane stride of rew4 is E*n)
@@ -45,6 +49,11 @@ struct KParams {
   // fp32 prefilter: map centre, validity radius, guarded squared thresholds (thr^2 + fp32 error bound)
   double cx, cy, rmax;
   float f_dp, f_dcmv;         // targets: dp; UAVs: max(dc + dt*v_max, 2 dp) (old position bounded through the new one)
+  // fp32 classification of the fast step kernel (step_fast_kernel.cuh): per radius the squared threshold rounded up /
+  // down to fp32 and the two coefficients of the guard g(R) = c1 R + c0 (R = largest |coordinate - centre| of the
+  // environment).  s_f <= t2_dn - g: certainly inside; s_f > t2_up + g: certainly outside; between: decided in fp64.
+  GuardK g_dp, g_2dp, g_dc, g_pf;
+  float r_fast;   // the fast kernel serves environments whose entities stay within this distance of the map centre
 };
 
 struct PmiDev {
@@ -55,6 +64,9 @@ struct PmiDev {
 
 typedef void (*StepKernelFn)(const KParams, const UavSimBuffers, const double *, int64_t, int64_t, int, int, double,
                              int, double *);
+struct ActEntry;
+typedef void (*FastKernelFn)(const KParams, const UavSimBuffers, const ActEntry *, int64_t, int64_t, int, double, int,
+                             double *);
 
 struct PmiTcDev;
 
@@ -73,6 +85,13 @@ struct uavsim {
   int epb, grid_max, nt;   // environments per CTA, resident CTAs, threads per CTA of the step kernel
   StepKernelFn step_fn[2];  // [MASKS]
   size_t smem_step;
+  // fast step kernel (64 x 64): [0] plain, [1] with masks / per-target counts
+  bool has_fast;
+  int step_path;            // 0 auto, 1 generic kernel, 2 fast kernel (error if unusable)
+  FastKernelFn fast_fn[2];
+  size_t smem_fast[2];
+  int fast_grid_max[2];
+  ActEntry *d_act;          // [na] per action: dt * rate (fp64), cos / sin of it (fp32)
   // pmi
   bool has_pmi;
   PmiDev pmi;

@@ -1,0 +1,79 @@
+// fast_math.cuh -- fp64 sine / cosine for headings (|h| <= pi plus one turn-rate step), shared by the step kernels.
+//
+// The reference evaluates math.cos / math.sin (glibc, < 1 ulp) on every heading once per step
+// (src/agent/uav.py:92-95, src/agent/target.py:35-38).  Headings are wrapped to [-pi, pi), so the general
+// argument reduction of the CUDA library routine (its slow path test, its call overhead: it is not inlined twice)
+// is dead weight here.  This is the classical scheme: k = rint(h * 2/pi), Cody-Waite reduction with a two-part
+// pi/2 (k <= 3: the first product is exact), the fdlibm kernel polynomials on [-pi/4, pi/4] with the reduction's
+// tail, quadrant fix-up.  Max error < 1 ulp (tests/test_fast_math.py checks it against libm on the host build of
+// this very file).  Compiles as plain C++ as well, so the host test exercises the same source.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#ifdef __CUDACC__
+#define FM_HD __host__ __device__ __forceinline__
+#else
+#define FM_HD static inline
+#endif
+
+FM_HD double fm_hi_as_double(uint32_t hi) {
+#ifdef __CUDA_ARCH__
+  return __hiloint2double((int)hi, 0);
+#else
+  uint64_t b = (uint64_t)hi << 32;
+  double d;
+  memcpy(&d, &b, 8);
+  return d;
+#endif
+}
+FM_HD uint32_t fm_hi_word(double x) {
+#ifdef __CUDA_ARCH__
+  return (uint32_t)__double2hiint(x);
+#else
+  uint64_t b;
+  memcpy(&b, &x, 8);
+  return (uint32_t)(b >> 32);
+#endif
+}
+
+// sin and cos of h for |h| < 4 (callers route anything else to the library routine)
+FM_HD void fm_sincos_small(double h, double *sn, double *cs) {
+  // k = rint(h * 2/pi) through the 1.5 * 2^52 shift; the low word of the shifted sum is k in two's complement
+  const double SHIFT = 6755399441055744.0;
+  const double ks = fma(h, 6.36619772367581382433e-01, SHIFT);
+#ifdef __CUDA_ARCH__
+  const int k = __double2loint(ks);
+#else
+  uint64_t kb;
+  memcpy(&kb, &ks, 8);
+  const int k = (int)(uint32_t)kb;
+#endif
+  const double kd = ks - SHIFT;
+  const double r0 = fma(-kd, 1.57079632673412561417e+00, h);  // first 33 bits of pi/2: the product is exact
+  const double w = kd * 6.07710050650619224932e-11;           // pi/2 - the above
+  const double x = r0 - w;
+  const double y = (r0 - x) - w;  // tail of the reduced argument
+  const double z = x * x;
+  // fdlibm __kernel_sin(x, y, 1)
+  const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03, S3 = -1.98412698298579493134e-04,
+               S4 = 2.75573137070700676789e-06, S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+  const double v = z * x;
+  const double rs = fma(z, fma(z, fma(z, fma(z, S6, S5), S4), S3), S2);
+  const double s = x - ((z * (0.5 * y - v * rs) - y) - v * S1);
+  // fdlibm __kernel_cos(x, y)
+  const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03, C3 = 2.48015872894767294178e-05,
+               C4 = -2.75573143513906633035e-07, C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+  const double rc = z * fma(z, fma(z, fma(z, fma(z, fma(z, C6, C5), C4), C3), C2), C1);
+  const uint32_t ix = fm_hi_word(x) & 0x7fffffffu;
+  double qx = 0.0;                                  // |x| < 0.3: 1 - (z/2 - (z rc - x y))
+  if (ix >= 0x3FD33333u) qx = (ix > 0x3fe90000u) ? 0.28125 : fm_hi_as_double(ix - 0x00200000u);  // x/4, low word cleared
+  const double hz = 0.5 * z - qx;
+  const double a = 1.0 - qx;
+  const double c = a - (hz - (z * rc - x * y));
+  // quadrant
+  const double s_ = (k & 1) ? c : s, c_ = (k & 1) ? s : c;
+  *sn = (k & 2) ? -s_ : s_;
+  *cs = ((k + 1) & 2) ? -c_ : c_;
+}

@@ -14,6 +14,7 @@
 #include "step_kernel.cuh"
 #include "pmi_kernel.cuh"
 #include "pmi_tc_kernel.cuh"
+#include "step_fast_kernel.cuh"
 #include "aux_kernels.cuh"
 #include "replay.cuh"
 
@@ -57,6 +58,28 @@ static float prefilter_threshold(double thr, double rmax) {
   float f = (float)v;
   if ((double)f < v) f = nextafterf(f, INFINITY);
   return nextafterf(f, INFINITY);
+}
+
+// Two-sided fp32 guard of the fast step kernel for one radius (same error model as prefilter_threshold, as a
+// function of R = largest |coordinate - centre| of an environment):
+//   bound(R) = 2 sqrt(2) thr u (2R + thr) + 2 u^2 (2R + thr)^2 + 3 u thr^2,  u = 2^-24
+// The kernel evaluates g = c1 R + c0 in fp32 and uses thr^2 rounded up + g / thr^2 rounded down - g; c1 and c0 carry
+// twice the bound (as the prefilter always has), the quadratic term at R = rmax, and room for their own rounding.
+static GuardK make_guard(double thr, double rmax) {
+  const double u = 1.0 / 16777216.0, r2 = 1.4142135623730951;
+  const double t2 = thr * thr;
+  GuardK g;
+  g.t2_up = (float)t2;
+  if ((double)g.t2_up < t2) g.t2_up = nextafterf(g.t2_up, INFINITY);
+  g.t2_dn = (float)t2;
+  if ((double)g.t2_dn > t2) g.t2_dn = nextafterf(g.t2_dn, -INFINITY);
+  const double c1 = 4 * r2 * thr * u;
+  const double c0 = 2 * r2 * u * t2 + 3 * u * t2 + 2 * u * u * (2 * rmax + thr) * (2 * rmax + thr);
+  const double ulp_t2 = (double)nextafterf((float)t2, INFINITY) - (double)(float)t2;
+  auto up = [](double v) { float f = (float)v; if ((double)f < v) f = nextafterf(f, INFINITY); return nextafterf(f, INFINITY); };
+  g.c1 = up(2 * c1 * (1 + 1e-6));
+  g.c0 = up(2 * c0 * (1 + 1e-6) + 4 * ulp_t2 + 1e-6);
+  return g;
 }
 
 #include "policy.cuh"
@@ -122,6 +145,18 @@ extern "C" int uavsim_create(const UavSimParams *p, int64_t n_envs, int64_t env_
     double r_uav = p->dc + fabs(k.dtv_u) * (1.0 + 1e-9);
     if (2.0 * p->dp > r_uav) r_uav = 2.0 * p->dp;
     k.f_dcmv = prefilter_threshold(r_uav, k.rmax);
+    k.g_pf = make_guard(r_uav, k.rmax);
+  }
+  k.g_dp = make_guard(p->dp, k.rmax);
+  k.g_2dp = make_guard(2 * p->dp, k.rmax);
+  k.g_dc = make_guard(p->dc, k.rmax);
+  {  // The fast kernel accumulates fp32 offsets between fp32 coordinates; a partner's coordinate rounding, up to
+     // R * 2^-24, reaches the observation divided by dp or dc.  Keep that below 2e-6 (the contract is 1e-5); beyond
+     // this radius an environment takes the fp64 path.
+    const double rmin = p->dp < p->dc ? p->dp : p->dc;
+    double rf = 2e-6 * 16777216.0 * rmin;
+    if (rf > k.rmax) rf = k.rmax;
+    k.r_fast = (float)rf;
   }
 
   // per action: dt * discrete_action(a) (src/agent/uav.py:73-81, :96) in the reference's evaluation order,
@@ -136,6 +171,13 @@ extern "C" int uavsim_create(const UavSimParams *p, int64_t n_envs, int64_t env_
   }
   CUDA_TRY(cudaMalloc(&h->d_dth, sizeof(double) * 3 * p->na));
   CUDA_TRY(cudaMemcpy(h->d_dth, dth, sizeof(double) * 3 * p->na, cudaMemcpyHostToDevice));
+  {  // the same table for the fast kernel: the angle in fp64, its cosine / sine in fp32
+    ActEntry *tab = (ActEntry *)malloc(sizeof(ActEntry) * p->na);
+    for (int a = 0; a < p->na; a++) { tab[a].dth = dth[3 * a]; tab[a].cd = (float)dth[3 * a + 1]; tab[a].sd = (float)dth[3 * a + 2]; }
+    CUDA_TRY(cudaMalloc(&h->d_act, sizeof(ActEntry) * p->na));
+    CUDA_TRY(cudaMemcpy(h->d_act, tab, sizeof(ActEntry) * p->na, cudaMemcpyHostToDevice));
+    free(tab);
+  }
   free(dth);
 
   // launch geometry of the step kernel: one thread per UAV, nt / n environments per CTA.  Small CTAs keep the
@@ -166,6 +208,22 @@ extern "C" int uavsim_create(const UavSimParams *p, int64_t n_envs, int64_t env_
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->step_fn[0], h->nt, h->smem_step));
   if (occ < 1) occ = 1;
   h->grid_max = h->sm_count * occ;
+  // fast kernel (step_fast_kernel.cuh): 64 x 64 swarms, one environment per 64-thread CTA
+  h->has_fast = (k.n == 64 && k.m == 64);
+  if (h->has_fast) {
+    h->fast_fn[0] = uavsim_step_fast_kernel<64, 64, false>;
+    h->fast_fn[1] = uavsim_step_fast_kernel<64, 64, true>;
+    h->smem_fast[0] = sizeof(FastSmem<64, 64, false>);
+    h->smem_fast[1] = sizeof(FastSmem<64, 64, true>);
+    for (int v = 0; v < 2; v++) {
+      int rc = raise_dynamic_smem((const void *)h->fast_fn[v], device, h->smem_fast[v]);
+      if (rc) return rc;
+      int o = 1;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, h->fast_fn[v], FAST_NT, h->smem_fast[v]));
+      h->fast_grid_max[v] = h->sm_count * (o < 1 ? 1 : o);
+      if (h->fast_grid_max[v] > h->grid_max) h->grid_max = h->fast_grid_max[v];  // statistics slots cover both kernels
+    }
+  }
   h->stat_slots = h->grid_max > 4096 ? h->grid_max : 4096;
   CUDA_TRY(cudaMalloc(&h->d_stats, sizeof(double) * 2 * h->stat_slots * STAT_W));
   CUDA_TRY(cudaMalloc(&h->d_stats8, sizeof(double) * 8));
@@ -187,7 +245,7 @@ extern "C" int uavsim_create(const UavSimParams *p, int64_t n_envs, int64_t env_
 extern "C" int uavsim_destroy(uavsim_t *h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
-  cudaFree(h->d_dth); cudaFree(h->d_stats); cudaFree(h->d_stats8); cudaFreeHost(h->h_stats8);
+  cudaFree(h->d_dth); cudaFree(h->d_act); cudaFree(h->d_stats); cudaFree(h->d_stats8); cudaFreeHost(h->h_stats8);
   cudaFree(h->d_pmi_blob); cudaFree(h->d_tc_tiles);
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_comp) cudaStreamDestroy(h->s_comp);
@@ -380,6 +438,13 @@ extern "C" int uavsim_set_pmi_path(uavsim_t *h, int path) {
   return 0;
 }
 
+extern "C" int uavsim_set_step_path(uavsim_t *h, int path) {
+  if (!h || path < 0 || path > 2) { SET_ERR("uavsim_set_step_path: bad argument"); return UAVSIM_ERR_ARG; }
+  if (path == 2 && !h->has_fast) { SET_ERR("uavsim_set_step_path: the fast step kernel serves 64 x 64 swarms only"); return UAVSIM_ERR_UNSUPPORTED; }
+  h->step_path = path;
+  return 0;
+}
+
 extern "C" int uavsim_set_pmi_weights(uavsim_t *h, const UavSimPmiWeights *w, void *stream) {
   if (!h || !w || !w->w0 || !w->b0 || !w->w1 || !w->b1 || !w->w2) { SET_ERR("uavsim_set_pmi_weights: NULL argument"); return UAVSIM_ERR_ARG; }
   const int H = w->hidden;
@@ -445,11 +510,28 @@ extern "C" int uavsim_set_pmi_weights(uavsim_t *h, const UavSimPmiWeights *w, vo
   return 0;
 }
 
+// The fast kernel moves whole arrays with bulk copies: every bound array it touches must be 16-byte aligned.
+static bool fast_path_usable(const uavsim_t *h) {
+  if (!h->has_fast || h->step_path == 1) return false;
+  const UavSimBuffers &b = h->buf;
+  const void *ptrs[] = {b.ux, b.uy, b.uh, b.ua, b.tx, b.ty, b.th, b.actions, b.obs, b.rew4};
+  for (const void *q : ptrs)
+    if (reinterpret_cast<uintptr_t>(q) & 15) return false;
+  return true;
+}
+
 // one step over the env range [e0, e0+cnt) on stream st
 static int launch_step_range(uavsim_t *h, int mode, double coop, int64_t e0, int64_t cnt, int done_flag, cudaStream_t st) {
-  const int64_t ngroups = (cnt + h->epb - 1) / h->epb;
-  const int grid = (int)(ngroups < h->grid_max ? ngroups : h->grid_max);
-  h->step_fn[h->buf.obs_mask ? 1 : 0]<<<grid, h->nt, h->smem_step, st>>>(h->kp, h->buf, h->d_dth, e0, cnt, h->epb, mode, coop, done_flag, h->d_stats);
+  if (fast_path_usable(h)) {
+    const int v = (h->buf.obs_mask || h->buf.tracker_cnt) ? 1 : 0;
+    const int grid = (int)(cnt < h->fast_grid_max[v] ? cnt : h->fast_grid_max[v]);
+    h->fast_fn[v]<<<grid, FAST_NT, h->smem_fast[v], st>>>(h->kp, h->buf, h->d_act, e0, cnt, mode, coop, done_flag, h->d_stats);
+  } else {
+    if (h->step_path == 2) { SET_ERR("uavsim_step: the fast step kernel needs 64 x 64 swarms and 16-byte aligned buffers"); return UAVSIM_ERR_UNSUPPORTED; }
+    const int64_t ngroups = (cnt + h->epb - 1) / h->epb;
+    const int grid = (int)(ngroups < h->grid_max ? ngroups : h->grid_max);
+    h->step_fn[h->buf.obs_mask ? 1 : 0]<<<grid, h->nt, h->smem_step, st>>>(h->kp, h->buf, h->d_dth, e0, cnt, h->epb, mode, coop, done_flag, h->d_stats);
+  }
   CUDA_TRY(cudaGetLastError());
   h->launches++;
   if (mode == UAVSIM_MODE_PMI && coop != 0.0) return pmi_launch(h, e0, cnt, coop, st, false);

@@ -156,6 +156,8 @@ class BatchedEnvironment:
         self._h, self._params, self._params_key = h, p, key
         self._pmi_key = None
         self._bind()
+        if getattr(self, "_step_path", 0):
+            _cabi.check(self._lib.uavsim_set_step_path(self._h, self._step_path), "uavsim_set_step_path")
 
     # ------------------------------------------------------------------ reference API
     def reset(self, config, seed=None):
@@ -224,6 +226,12 @@ class BatchedEnvironment:
         self._pmi_path = int(path)
         if self._h is not None:
             _cabi.check(self._lib.uavsim_set_pmi_path(self._h, self._pmi_path), "uavsim_set_pmi_path")
+
+    def set_step_path(self, path):
+        """0 = automatic, 1 = generic step kernel, 2 = fast 64 x 64 step kernel (uavsim_set_step_path)."""
+        self._step_path = int(path)
+        if self._h is not None:
+            _cabi.check(self._lib.uavsim_set_step_path(self._h, self._step_path), "uavsim_set_step_path")
 
     def _sync_weights(self, config):
         u = config.get("uav", {})
