@@ -38,11 +38,28 @@ FM_HD uint32_t fm_hi_word(double x) {
 #endif
 }
 
+// The coefficients sit in constant memory on the device: an fp64 immediate costs two extra instructions per use,
+// a constant-bank operand none.
+#define FM_COEFFS                                                                                                       \
+  {6755399441055744.0, 6.36619772367581382433e-01, 1.57079632673412561417e+00, 6.07710050650619224932e-11,              \
+   -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04, 2.75573137070700676789e-06,    \
+   -2.50507602534068634195e-08, 1.58969099521155010221e-10, 4.16666666666666019037e-02, -1.38888888888741095749e-03,    \
+   2.48015872894767294178e-05, -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11}
+#ifdef __CUDACC__
+__constant__ double fm_dev_coeff[16] = FM_COEFFS;
+#endif
+static const double fm_host_coeff[16] = FM_COEFFS;
+#ifdef __CUDA_ARCH__
+#define FM_K(i) fm_dev_coeff[i]
+#else
+#define FM_K(i) fm_host_coeff[i]
+#endif
+
 // sin and cos of h for |h| < 4 (callers route anything else to the library routine)
 FM_HD void fm_sincos_small(double h, double *sn, double *cs) {
   // k = rint(h * 2/pi) through the 1.5 * 2^52 shift; the low word of the shifted sum is k in two's complement
-  const double SHIFT = 6755399441055744.0;
-  const double ks = fma(h, 6.36619772367581382433e-01, SHIFT);
+  const double SHIFT = FM_K(0);
+  const double ks = fma(h, FM_K(1), SHIFT);
 #ifdef __CUDA_ARCH__
   const int k = __double2loint(ks);
 #else
@@ -51,20 +68,18 @@ FM_HD void fm_sincos_small(double h, double *sn, double *cs) {
   const int k = (int)(uint32_t)kb;
 #endif
   const double kd = ks - SHIFT;
-  const double r0 = fma(-kd, 1.57079632673412561417e+00, h);  // first 33 bits of pi/2: the product is exact
-  const double w = kd * 6.07710050650619224932e-11;           // pi/2 - the above
+  const double r0 = fma(-kd, FM_K(2), h);  // first 33 bits of pi/2: the product is exact
+  const double w = kd * FM_K(3);           // pi/2 - the above
   const double x = r0 - w;
   const double y = (r0 - x) - w;  // tail of the reduced argument
   const double z = x * x;
   // fdlibm __kernel_sin(x, y, 1)
-  const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03, S3 = -1.98412698298579493134e-04,
-               S4 = 2.75573137070700676789e-06, S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+  const double S1 = FM_K(4), S2 = FM_K(5), S3 = FM_K(6), S4 = FM_K(7), S5 = FM_K(8), S6 = FM_K(9);
   const double v = z * x;
   const double rs = fma(z, fma(z, fma(z, fma(z, S6, S5), S4), S3), S2);
   const double s = x - ((z * (0.5 * y - v * rs) - y) - v * S1);
   // fdlibm __kernel_cos(x, y)
-  const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03, C3 = 2.48015872894767294178e-05,
-               C4 = -2.75573143513906633035e-07, C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+  const double C1 = FM_K(10), C2 = FM_K(11), C3 = FM_K(12), C4 = FM_K(13), C5 = FM_K(14), C6 = FM_K(15);
   const double rc = z * fma(z, fma(z, fma(z, fma(z, fma(z, C6, C5), C4), C3), C2), C1);
   const uint32_t ix = fm_hi_word(x) & 0x7fffffffu;
   double qx = 0.0;                                  // |x| < 0.3: 1 - (z/2 - (z rc - x y))

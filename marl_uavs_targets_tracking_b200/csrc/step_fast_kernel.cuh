@@ -17,7 +17,10 @@
 //     each guarded radius; three short walks consume them: targets (observation + tracking reward + coverage),
 //     communication partners (new record if the partner moved first, old record otherwise: src/agent/uav.py:124-147
 //     in the update order of src/environment.py:133-138), and duplicate-tracking / neighbour partners
-//     (src/agent/uav.py:214-229, :305).
+//     (src/agent/uav.py:214-229, :305).  UAV records are stored two per SLOT (partners 2b and 2b+1 side by side in
+//     the halves of the packed fp32 registers): the UAV walks visit slots, not partners, and evaluate both partners
+//     of a slot with f32x2 arithmetic and 0/1 weights -- a swarm that flies in formation has its partners in runs of
+//     consecutive indices, so the trips nearly halve exactly when the candidate lists are long.
 //   * fp64 sine / cosine of the headings by fm_sincos_small (fast_math.cuh) instead of the library call.
 // Everything that is not a pair test (kinematics, reflection, boundary term, normalisation, cooperative reward,
 // statistics) follows the generic kernel line by line.
@@ -35,47 +38,57 @@ struct ActEntry {
   float cd, sd;
 };
 
+// two UAVs (2b, 2b+1) side by side: the halves of the packed f32x2 operands
+struct __align__(16) SlotRec {
+  float4 pos;  // {x0, x1, y0, y1} relative to the map centre
+  float4 hd;   // {cos h0, cos h1, sin h0, sin h1}
+  float2 a;    // action index as float
+  float2 pad;
+};
+// two targets: positions, then cos / sin of the heading times tv / uv (src/agent/uav.py:115-116)
+struct __align__(16) TSlot {
+  float4 pos;  // {x0, x1, y0, y1}
+  float4 vel;  // {vx0, vx1, vy0, vy1}
+};
+
 template <int N, int M, bool AUX>
 struct __align__(128) FastSmem {
   // inputs of the current environment (bulk-loaded)
   double ux[N], uy[N], uh[N];
   double tx[M], ty[M], th[M];
   int32_t ua[N], act[N];
-  // outputs (bulk-stored)
+  // new state (bulk-stored)
   double oux[N], ouy[N], ouh[N];
   double otx[M], oty[M], oth[M];
   int32_t oua[N];
-  float rew[4][N];
-  float obs[N * 12];
-  // working set of the pair phase (fp32, positions relative to the map centre)
-  float4 pn2[N / 2];   // new UAV positions, two per entry {x0, x1, y0, y1}: operands of the packed prefilter
-  float4 tp2[M / 2];   // target positions, same pairing
-  float4 recn[N][2];   // UAV after its move  {x, y, cos h, sin h} {a, -, -, -}
-  float4 reco[N][2];   // UAV before its move (same layout; reco - recn is a compile-time offset)
-  float4 trec[M];      // target {x, y, cos h * tv/uv, sin h * tv/uv}
-  double xo[N], yo[N]; // fp64 positions before the move (exact path only)
-  double raw[N];       // weighted raw reward of every UAV (neighbour mean)
+  // working set of the pair phase (fp32, positions relative to the map centre).  Once the pair phase is over
+  // (second CTA barrier) the same bytes stage the outputs: observations [N][12] over the UAV slots, the four reward
+  // planes [4][N] over the target slots.
+  SlotRec slotn[N / 2];  // UAVs after their move
+  SlotRec sloto[N / 2];  // UAVs before their move (sloto - slotn is a compile-time offset)
+  TSlot tslot[M / 2];
+  double xo[N], yo[N];   // fp64 positions before the move (exact path only)
+  float raw[N];          // weighted raw reward of every UAV (neighbour mean)
   int32_t tcnt[AUX ? M : 1];
-  uint32_t cover[2][2];  // per warp: targets with a UAV strictly inside dp
+  uint32_t cover[2][2];  // per warp: targets with a UAV strictly inside dp (even / odd word)
   uint32_t rmax[2];      // per warp: largest |coordinate - centre| as float bits
   unsigned long long mbar;
 };
+static_assert(sizeof(SlotRec) == 48 && sizeof(TSlot) == 32, "slot layout");
 
-// ---- single-thread async-copy instructions, issued by a CONVERGED warp and predicated on one elected lane inside the
-//      asm: under a divergent `if (t == 0)` every operand of these uniform-datapath instructions goes through a
-//      per-instruction waterfall loop (see pmi_tc_kernel.cuh) ----
-__device__ __forceinline__ void sf_expect_tx(uint32_t lead, uint32_t bar, uint32_t bytes) {
-  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
-               "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes), "r"(lead) : "memory");
+// ---- single-thread async-copy instructions.  They are issued from `if (warp == 0) if (elect_one())`: ptxas
+//      recognises a branch on the predicate of ELECT as a single-thread region and emits the copies back to back on
+//      the uniform datapath.  Under `if (t == 0)`, or predicated on an elected lane inside the asm, every copy was
+//      wrapped in a VOTEU / ELECT / BRA.U.ANY waterfall of ~14 instructions (profiles/r2_* history). ----
+__device__ __forceinline__ void sf_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void sf_bulk_g2s(uint32_t lead, uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\t"
-               "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "r"(lead) : "memory");
+__device__ __forceinline__ void sf_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void sf_bulk_s2g(uint32_t lead, void *dst, uint32_t src, uint32_t bytes) {
-  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t"
-               "@q cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\t}" ::"l"(dst), "r"(src), "r"(bytes), "r"(lead) : "memory");
+__device__ __forceinline__ void sf_bulk_s2g(void *dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ uint32_t sf_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void sf_mbar_wait(uint32_t bar, uint32_t parity) {
@@ -114,6 +127,20 @@ __device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
 }
 __device__ __forceinline__ float f2_lo(uint64_t v) { return __uint_as_float((uint32_t)v); }
 __device__ __forceinline__ float f2_hi(uint64_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
+// Packed 0 / 1 weights {a0 <= b, a1 <= b}.  (Written with setp / selp on the bit patterns: with `set.le.f32.f32`
+// feeding the low half of a packed operand, ptxas 12.9 turned the set into FSETP + SEL ..., 0x1 -- the INTEGER one, a
+// denormal as a float -- and every even partner lost its weight.  tools/sass_lines.py --listing shows the encoding.)
+__device__ __forceinline__ uint64_t sf_le2(float a0, float a1, float b) {
+  uint32_t lo, hi;
+  asm("{\n\t.reg .pred p, q;\n\t"
+      "setp.le.f32 p, %2, %4;\n\t"
+      "setp.le.f32 q, %3, %4;\n\t"
+      "selp.b32 %0, 0x3f800000, 0, p;\n\t"
+      "selp.b32 %1, 0x3f800000, 0, q;\n\t}"
+      : "=r"(lo), "=r"(hi) : "f"(a0), "f"(a1), "f"(b));
+  return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+__device__ __forceinline__ float sf_le(float a, float b) { return (a <= b) ? 1.0f : 0.0f; }
 __device__ __forceinline__ int sf_msb(uint32_t w) {  // index of the highest set bit (w != 0): one FLO
   int r;
   asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(w));
@@ -126,22 +153,21 @@ __device__ __forceinline__ float sf_rcp(float x) {
 }
 
 // Candidate sets are kept as an EVEN and an ODD word: bit b of the even word is partner 2b, of the odd word partner
-// 2b+1.  Both words span the whole index range, so a lane's candidates split evenly between them and the two walks
-// (one per word, each as long as its busiest lane) together take about as many trips as the busiest lane has
-// candidates -- with one word per 32 consecutive partners a swarm flying in index order needed up to 1.5 x that.
+// 2b+1 (the two partners of slot b).
 //
-// Sign-bit prefilter over 64 partner positions (32 pairs {x0, x1, y0, y1}) against one or two guarded squared radii:
-// the partner's bit is set iff fma(dx, dx, fma(dy, dy, -thr)) < 0.
-template <bool TWO>
-__device__ __forceinline__ void prefilter64(const float4 *__restrict__ pf, float xf, float yf, float thrA, float thrB,
+// Sign-bit prefilter over 64 partner positions (32 pairs {x0, x1, y0, y1}, `stride` bytes apart) against one or two
+// guarded squared radii: the partner's bit is set iff fma(dx, dx, fma(dy, dy, -thr)) < 0.
+template <bool TWO, int STRIDE>
+__device__ __forceinline__ void prefilter64(const void *__restrict__ pf, float xf, float yf, float thrA, float thrB,
                                             uint32_t &aE, uint32_t &aO, uint32_t &bE, uint32_t &bO) {
   const uint64_t xf2 = pack2(xf, xf), yf2 = pack2(yf, yf), nA = pack2(-thrA, -thrA), nB = pack2(-thrB, -thrB);
+  const unsigned char *base = reinterpret_cast<const unsigned char *>(pf);
   uint32_t ae = 0, ao = 0, be = 0, bo = 0;
 #pragma unroll 1
   for (int k = 0; k < 32; k += 4) {
 #pragma unroll
     for (int u = 0; u < 4; u++) {
-      const ulonglong2 p = reinterpret_cast<const ulonglong2 *>(pf)[k + u];
+      const ulonglong2 p = *reinterpret_cast<const ulonglong2 *>(base + (k + u) * STRIDE);
       const uint64_t dx = f2_sub(p.x, xf2), dy = f2_sub(p.y, yf2);
       const uint64_t tA = f2_fma(dx, dx, f2_fma(dy, dy, nA));
       ae = __funnelshift_l((uint32_t)tA, ae, 1);
@@ -171,16 +197,21 @@ __device__ __forceinline__ uint64_t sf_interleave(uint32_t e, uint32_t o) {
   return spread(e) | (spread(o) << 1);
 }
 
+// what the pair phase produces for one UAV
+struct FastAgent {
+  float ob[9];        // communication part (5) and observation part (4) of the local state
+  float tt, dup;      // raw tracking reward, raw duplicate punishment
+  uint32_t nb[2];     // neighbour set d <= dp (even / odd word)
+  uint32_t cov[2];    // targets strictly inside dp (even / odd word)
+};
+
 // ------------------------------------------------------------------------------------------------
 // exact path: the reference's arithmetic pair by pair in fp64, including the min(dist, 1) row weights of
 // src/agent/uav.py:162-186.  Taken by a UAV that met an ambiguous pair, by UAVs within 2 m of the origin in both
 // coordinates (the only place where a row weight differs from 1) and by every UAV of an environment with an
-// entity outside the radius the guard is proven for.  Cold: never inlined; its constants and mask pointers travel
-// by value (a reference to the kernel's parameter block would force a copy of the whole block into local memory at
-// kernel entry) and its results come back through the UAV's own slots of the output staging area (a pointer to
-// registers of the caller would push them into local memory on the hot path as well):
-//   obs[12 i .. +8] the nine list entries of the local state, obs[12 i + 9] = tt, obs[12 i + 10] = dup,
-//   rew[0][i], rew[1][i] = neighbour words (even, odd), rew[2][i], rew[3][i] = coverage words.
+// entity outside the radius the fast path serves.  Cold: never inlined; its constants and mask pointers travel by
+// value (a reference to the kernel's parameter block would force a copy of the whole block into local memory at
+// kernel entry) and the result lands in a struct that only the cold branch of the caller touches.
 // ------------------------------------------------------------------------------------------------
 struct ExactK {
   double s_dp_le, s_dp_lt, s_2dp_le, s_dc_le, dp, dc, two_dp;
@@ -190,11 +221,11 @@ struct MaskPtrs {
   uint8_t *obs_mask, *comm_mask, *nbr_mask, *dup_mask, *cover_mask;
 };
 template <int N, int M, bool AUX>
-__device__ __noinline__ void fast_agent_exact(const ExactK P, const MaskPtrs B, FastSmem<N, M, AUX> &S, int i,
-                                              int64_t mrow_t, int64_t mrow_u) {
+__device__ __noinline__ void fast_agent_exact(const ExactK P, const MaskPtrs B, const FastSmem<N, M, AUX> &S, int i,
+                                              int64_t mrow_t, int64_t mrow_u, FastAgent *Op) {
   const double xi = S.oux[i], yi = S.ouy[i];
-  const float4 me = S.recn[i][0];
-  const double chi = (double)me.z, shi = (double)me.w;
+  const float *own = reinterpret_cast<const float *>(&S.slotn[i >> 1]) + (i & 1);
+  const double chi = (double)own[4], shi = (double)own[6];
   const int ai = S.oua[i];
   double tt = 0, o0 = 0, o1 = 0, o2 = 0, o3 = 0;
   int nobs = 0;
@@ -208,8 +239,8 @@ __device__ __noinline__ void fast_agent_exact(const ExactK P, const MaskPtrs B, 
     if (hit) {
       const double d = sqrt(d2);
       tt += 1 + (P.dp - d) / P.dp;  // uav.py:208
-      const float4 tr = S.trec[t];
-      double rx = dx / P.dp, ry = dy / P.dp, vx = (double)tr.z - chi, vy = (double)tr.w - shi;
+      const float *tr = reinterpret_cast<const float *>(&S.tslot[t >> 1]) + (t & 1);
+      double rx = dx / P.dp, ry = dy / P.dp, vx = (double)tr[4] - chi, vy = (double)tr[6] - shi;
       const double wx = rx - xi, wy = ry - yi, w2 = wx * wx + wy * wy;  // uav.py:174-180
       if (w2 < 1.0) { const double w = sqrt(w2); rx /= w; ry /= w; vx /= w; vy /= w; }
       o0 += rx; o1 += ry; o2 += vx; o3 += vy;
@@ -230,50 +261,57 @@ __device__ __noinline__ void fast_agent_exact(const ExactK P, const MaskPtrs B, 
     if (hit_dup) { const double d = sqrt(d2n); dup += -0.5 * exp((P.two_dp - d) / P.two_dp); }  // uav.py:226
     if (hit_nbr) nb[j & 1] |= 1u << (j >> 1);
     double dxc, dyc, d2c;
-    float4 r0;
-    float aj;
-    if (j < i) { dxc = dxn; dyc = dyn; d2c = d2n; r0 = S.recn[j][0]; aj = S.recn[j][1].x; }
-    else { dxc = S.xo[j] - xi; dyc = S.yo[j] - yi; d2c = dxc * dxc + dyc * dyc; r0 = S.reco[j][0]; aj = S.reco[j][1].x; }
+    const float *rj;  // partner's record: after its move if it moved first, before it otherwise
+    if (j < i) { dxc = dxn; dyc = dyn; d2c = d2n; rj = reinterpret_cast<const float *>(&S.slotn[j >> 1]) + (j & 1); }
+    else { dxc = S.xo[j] - xi; dyc = S.yo[j] - yi; d2c = dxc * dxc + dyc * dyc; rj = reinterpret_cast<const float *>(&S.sloto[j >> 1]) + (j & 1); }
     const bool hit_c = d2c <= P.s_dc_le;
     if (AUX && B.obs_mask) { B.comm_mask[mrow_u + j] = hit_c; B.nbr_mask[mrow_u + j] = hit_nbr; B.dup_mask[mrow_u + j] = hit_dup; }
     if (hit_c) {
-      double rx = dxc / P.dc, ry = dyc / P.dc, vx = (double)r0.z - chi, vy = (double)r0.w - shi;
-      double da = ((double)aj - (double)ai) / (double)P.na;
+      double rx = dxc / P.dc, ry = dyc / P.dc, vx = (double)rj[4] - chi, vy = (double)rj[6] - shi;
+      double da = ((double)rj[8] - (double)ai) / (double)P.na;
       const double wx = rx - xi, wy = ry - yi, w2 = wx * wx + wy * wy;
       if (w2 < 1.0) { const double w = sqrt(w2); rx /= w; ry /= w; vx /= w; vy /= w; da /= w; }
       c0 += rx; c1 += ry; c2 += vx; c3 += vy; c4 += da;
       ncomm++;
     }
   }
-  float *ob = S.obs + i * 12;
+  FastAgent &O = *Op;
   if (ncomm) {
     const double k = (double)ncomm;
-    ob[0] = (float)(c0 / k); ob[1] = (float)(c1 / k); ob[2] = (float)(c2 / k); ob[3] = (float)(c3 / k); ob[4] = (float)(c4 / k);
+    O.ob[0] = (float)(c0 / k); O.ob[1] = (float)(c1 / k); O.ob[2] = (float)(c2 / k); O.ob[3] = (float)(c3 / k); O.ob[4] = (float)(c4 / k);
   } else {
-    ob[0] = ob[1] = ob[2] = ob[3] = ob[4] = -1.f;
+    O.ob[0] = O.ob[1] = O.ob[2] = O.ob[3] = O.ob[4] = -1.f;
   }
   if (nobs) {
     const double k = (double)nobs;
-    ob[5] = (float)(o0 / k); ob[6] = (float)(o1 / k); ob[7] = (float)(o2 / k); ob[8] = (float)(o3 / k);
+    O.ob[5] = (float)(o0 / k); O.ob[6] = (float)(o1 / k); O.ob[7] = (float)(o2 / k); O.ob[8] = (float)(o3 / k);
   } else {
-    ob[5] = ob[6] = ob[7] = ob[8] = -1.f;
+    O.ob[5] = O.ob[6] = O.ob[7] = O.ob[8] = -1.f;
   }
-  ob[9] = (float)tt; ob[10] = (float)dup;
-  S.rew[0][i] = __uint_as_float(nb[0]); S.rew[1][i] = __uint_as_float(nb[1]);
-  S.rew[2][i] = __uint_as_float(cov[0]); S.rew[3][i] = __uint_as_float(cov[1]);
+  O.tt = (float)tt; O.dup = (float)dup;
+  O.nb[0] = nb[0]; O.nb[1] = nb[1];
+  O.cov[0] = cov[0]; O.cov[1] = cov[1];
 }
 
-// sin / cos of a heading: the wrapped range takes the inline routine, anything else the library one
+// sin / cos of a heading: the wrapped range takes the inline routine, anything else the library one (whose pointer
+// arguments stay inside the cold branch)
 __device__ __forceinline__ void heading_sincos(double h, double &s, double &c) {
-  if (fabs(h) < 4.0) fm_sincos_small(h, &s, &c);
-  else sincos_shared(h, &s, &c);
+  if (fabs(h) < 4.0) {
+    double s1, c1;
+    fm_sincos_small(h, &s1, &c1);
+    s = s1; c = c1;
+  } else {
+    double s2, c2;
+    sincos_shared(h, &s2, &c2);
+    s = s2; c = c2;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
 #ifndef FAST_CTAS_PER_SM
-#define FAST_CTAS_PER_SM 11
+#define FAST_CTAS_PER_SM 14
 #endif
 template <int N, int M, bool AUX>
 __global__ void __launch_bounds__(FAST_NT, FAST_CTAS_PER_SM)
@@ -281,25 +319,29 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
                         int64_t env_count, int mode, double coop, int done_flag, double *__restrict__ stats_partial) {
   static_assert(N == 64 && M == 64 && FAST_NT == 64, "one thread per UAV and per target");
   typedef FastSmem<N, M, AUX> SmemT;
-  static_assert(offsetof(SmemT, reco) - offsetof(SmemT, recn) == sizeof(float4) * 2 * N, "record offset");
+  static_assert(offsetof(SmemT, sloto) - offsetof(SmemT, slotn) == sizeof(SlotRec) * (N / 2), "record offset");
+  static_assert(sizeof(SlotRec) * N >= sizeof(float) * 12 * N && sizeof(TSlot) * (M / 2) >= sizeof(float) * 4 * N, "output staging");
   extern __shared__ __align__(128) unsigned char fast_smem_raw[];
   SmemT &S = *reinterpret_cast<SmemT *>(fast_smem_raw);
+  float *const s_obs = reinterpret_cast<float *>(S.slotn);   // [N][12], after the pair phase
+  float *const s_rew = reinterpret_cast<float *>(S.tslot);   // [4][N],  after the pair phase
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const uint32_t bar = sf_smem(&S.mbar);
   constexpr uint32_t IN_BYTES = 3 * N * 8 + 3 * M * 8 + 2 * N * 4;
+  constexpr uint32_t OLD_OFF = (uint32_t)(sizeof(SlotRec) * (N / 2));
   const bool pmi_pending = (mode == UAVSIM_MODE_PMI) && (coop != 0.0);
 
-  // warp 0, converged: the eight input arrays of environment e
-  auto issue_loads = [&](uint32_t lead, int64_t e) {
-    sf_expect_tx(lead, bar, IN_BYTES);
-    sf_bulk_g2s(lead, sf_smem(S.ux), B.ux + e * N, N * 8, bar);
-    sf_bulk_g2s(lead, sf_smem(S.uy), B.uy + e * N, N * 8, bar);
-    sf_bulk_g2s(lead, sf_smem(S.uh), B.uh + e * N, N * 8, bar);
-    sf_bulk_g2s(lead, sf_smem(S.tx), B.tx + e * M, M * 8, bar);
-    sf_bulk_g2s(lead, sf_smem(S.ty), B.ty + e * M, M * 8, bar);
-    sf_bulk_g2s(lead, sf_smem(S.th), B.th + e * M, M * 8, bar);
-    sf_bulk_g2s(lead, sf_smem(S.ua), B.ua + e * N, N * 4, bar);
-    sf_bulk_g2s(lead, sf_smem(S.act), B.actions + e * N, N * 4, bar);
+  // one elected thread of warp 0: the eight input arrays of environment e
+  auto issue_loads = [&](int64_t e) {
+    sf_expect_tx(bar, IN_BYTES);
+    sf_bulk_g2s(sf_smem(S.ux), B.ux + e * N, N * 8, bar);
+    sf_bulk_g2s(sf_smem(S.uy), B.uy + e * N, N * 8, bar);
+    sf_bulk_g2s(sf_smem(S.uh), B.uh + e * N, N * 8, bar);
+    sf_bulk_g2s(sf_smem(S.tx), B.tx + e * M, M * 8, bar);
+    sf_bulk_g2s(sf_smem(S.ty), B.ty + e * M, M * 8, bar);
+    sf_bulk_g2s(sf_smem(S.th), B.th + e * M, M * 8, bar);
+    sf_bulk_g2s(sf_smem(S.ua), B.ua + e * N, N * 4, bar);
+    sf_bulk_g2s(sf_smem(S.act), B.actions + e * N, N * 4, bar);
   };
 
   if (t == 0) {
@@ -307,10 +349,8 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  uint32_t lead = 0;
-  if (warp == 0) {
-    lead = elect_one();
-    if ((int64_t)blockIdx.x < env_count) issue_loads(lead, env_begin + blockIdx.x);
+  if (warp == 0 && (int64_t)blockIdx.x < env_count) {
+    if (elect_one()) issue_loads(env_begin + blockIdx.x);
   }
 
   const int64_t plane = P.E * N;
@@ -319,13 +359,18 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
   double st_r = 0, st_tt = 0, st_bp = 0, st_dup = 0, st_cov = 0, st_envs = 0;
   int st_cmax = 0;
   uint32_t parity = 0;
-  // partners below the own index inside the even / odd word (2b < t, 2b + 1 < t) and the own bit
-  const uint32_t ltE = low_bits((t + 1) >> 1), ltO = low_bits(t >> 1);
-  const uint32_t selfE = (t & 1) ? 0u : (1u << (t >> 1)), selfO = (t & 1) ? (1u << (t >> 1)) : 0u;
+  const int ih = t >> 1, ic = t & 1;   // own slot and place in it
+  // Slots below ihx hold partners that moved before this UAV (their NEW records are observed), slots from ihx on
+  // partners that move after it (OLD records); the own slot follows its other occupant (2 ih < t iff t is odd).
+  const int ihx = ih + ic;
 
   for (int64_t k = blockIdx.x; k < env_count; k += gridDim.x) {
     const int64_t e = env_begin + k;
-    if (lead) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous outputs have left shared memory
+    // The thread that committed the previous outputs waits until they have left shared memory.  (Bulk groups belong
+    // to the issuing thread: elect.sync with a full mask picks the same lane every time.)
+    if (warp == 0) {
+      if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
     __syncthreads();
     sf_mbar_wait(bar, parity);
     parity ^= 1;
@@ -342,11 +387,11 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
       if (0 > y || y > P.y_max) { h = -h; sh = -sh; }
       else if (x < 0 || x > P.x_max) { h = (h > 0) ? (PI_D - h) : (-PI_D - h); ch = -ch; }
       S.otx[t] = x; S.oty[t] = y; S.oth[t] = h;
-      const float xf = (float)(x - P.cx), yf = (float)(y - P.cy);
-      // cos(target.h) * target.v_max / self.v_max  (src/agent/uav.py:115-116)
-      S.trec[t] = make_float4(xf, yf, (float)(ch * P.tv_over_uv), (float)(sh * P.tv_over_uv));
-      EnvView::put_pair(S.tp2, t, xf, yf);
-      rabs = fmaxf(fabsf(xf), fabsf(yf));
+      const float txf = (float)(x - P.cx), tyf = (float)(y - P.cy);
+      float *ts = reinterpret_cast<float *>(&S.tslot[ih]) + ic;
+      ts[0] = txf; ts[2] = tyf;
+      ts[4] = (float)(ch * P.tv_over_uv); ts[6] = (float)(sh * P.tv_over_uv);
+      rabs = fmaxf(fabsf(txf), fabsf(tyf));
       if (AUX) S.tcnt[t] = 0;
     }
     // ---- phase 0b: UAV t (src/agent/uav.py:73-99) ----
@@ -361,8 +406,8 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
       const float cof = (float)ch, sof = (float)sh;
       const float xof = (float)(x - P.cx), yof = (float)(y - P.cy);
       S.xo[t] = x; S.yo[t] = y;
-      S.reco[t][0] = make_float4(xof, yof, cof, sof);
-      S.reco[t][1].x = (float)a_old;
+      float *so = reinterpret_cast<float *>(&S.sloto[ih]) + ic;
+      so[0] = xof; so[2] = yof; so[4] = cof; so[6] = sof; so[8] = (float)a_old;
       x += P.dtv_u * ch;
       y += P.dtv_u * sh;
       double dh;
@@ -384,9 +429,8 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
       xf = (float)(x - P.cx); yf = (float)(y - P.cy);
       xl = (float)((x - P.cx) - (double)xf); yl = (float)((y - P.cy) - (double)yf);
       S.oux[t] = x; S.ouy[t] = y; S.ouh[t] = h; S.oua[t] = act;
-      S.recn[t][0] = make_float4(xf, yf, chf, shf);
-      S.recn[t][1].x = (float)act;
-      EnvView::put_pair(S.pn2, t, xf, yf);
+      float *sn = reinterpret_cast<float *>(&S.slotn[ih]) + ic;
+      sn[0] = xf; sn[2] = yf; sn[4] = chf; sn[6] = shf; sn[8] = (float)act;
       rabs = fmaxf(fmaxf(rabs, fmaxf(fabsf(xf), fabsf(yf))), fmaxf(fabsf(xof), fabsf(yof)));
       // fp32 sums of action indices are exact only for small integers: anything else takes the exact path
       if ((unsigned)act >= 4096u || (unsigned)a_old >= 4096u) rabs = __int_as_float(0x7f800000);
@@ -398,7 +442,9 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
       if (lane == 0) S.rmax[warp] = rm;
     }
     __syncthreads();
-    if (warp == 0 && k + gridDim.x < env_count) issue_loads(lead, e + gridDim.x);  // next environment, behind the pair phase
+    if (warp == 0 && k + gridDim.x < env_count) {  // next environment, behind the pair phase
+      if (elect_one()) issue_loads(e + gridDim.x);
+    }
 
     // ---- phase 1: pair tests, observation, raw reward ----
     const float R = __uint_as_float(max(S.rmax[0], S.rmax[1]));
@@ -418,43 +464,39 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
       const float T2_hi = __fadd_ru(P.g_2dp.t2_up, g_2dp), T2_lo = __fadd_rd(P.g_2dp.t2_dn, -g_2dp);
       const float Tc_hi = __fadd_ru(P.g_dc.t2_up, g_dc), Tc_lo = __fadd_rd(P.g_dc.t2_dn, -g_dc);
       const float Tf_hi = __fadd_ru(P.g_pf.t2_up, g_pf);
-      // ambiguity trackers: the largest squared distance among the pairs each walk ACCEPTS as inside a radius; a
-      // walk is unambiguous iff that stays at or below the radius' lower guard
-      float smax_t = 0.f, smax_c = 0.f, smax_d = 0.f, smax_n = 0.f;
-      const uint64_t me2 = pack2(xf, yf);
+      const uint64_t xf2 = pack2(xf, xf), yf2 = pack2(yf, yf);
+      bool amb = false;
 
       // -- targets: observe_target (uav.py:101-122), tracking reward (uav.py:199-212), coverage (environment.py:246-253)
       {
         uint32_t d0, d1;
-        prefilter64<false>(S.tp2, xf, yf, Tp_hi, 0.f, cvE, cvO, d0, d1);
+        prefilter64<false, (int)sizeof(TSlot)>(S.tslot, xf, yf, Tp_hi, 0.f, cvE, cvO, d0, d1);
         const int nobs = __popc(cvE) + __popc(cvO);
-        uint64_t od = 0, ov = 0;  // packed sums {dx, dy}, {vx, vy}
-        float ttacc = 0;
+        float ox = 0, oy = 0, ovx = 0, ovy = 0, ttacc = 0, smax_t = 0;
 #pragma unroll
         for (int par = 0; par < 2; par++) {
           uint32_t w = par ? cvO : cvE;
-          const ulonglong2 *rec = reinterpret_cast<const ulonglong2 *>(S.trec + par);
+          const float *rec = reinterpret_cast<const float *>(S.tslot) + par;
 #pragma unroll 1
           while (w) {
             const int b = sf_msb(w);
             w ^= 1u << b;
-            const ulonglong2 tr = rec[2 * b];    // {x, y}, {vx, vy}
-            const uint64_t d = f2_sub(tr.x, me2);
-            const uint64_t q = f2_mul(d, d);
-            const float s = f2_lo(q) + f2_hi(q);
-            smax_t = fmaxf(smax_t, s);
-            od = f2_add(od, d);
-            ov = f2_add(ov, tr.y);
+            const float *r = rec + 8 * b;
+            const float dx = r[0] - xf, dy = r[2] - yf;
+            const float s = fmaf(dx, dx, dy * dy);
+            smax_t = fmaxf(smax_t, s);  // every candidate is accepted: unambiguous iff all of them are below the lower guard
+            ox += dx; oy += dy; ovx += r[4]; ovy += r[6];
             ttacc = fmaf(fast_sqrtf(s), -inv_dp_f, ttacc);  // sum of (dp - d)/dp - 1
           }
         }
+        amb |= smax_t > Tp_lo;
         if (nobs) {
           const float kf = (float)nobs, rk = sf_rcp(kf);
           // the own coordinate's fp32 rounding is common to every row: taken out of the mean exactly
-          o5 = fmaf(f2_lo(od), rk, -xl) * inv_dp_f;
-          o6 = fmaf(f2_hi(od), rk, -yl) * inv_dp_f;
-          o7 = fmaf(f2_lo(ov), rk, -chf);
-          o8 = fmaf(f2_hi(ov), rk, -shf);
+          o5 = fmaf(ox, rk, -xl) * inv_dp_f;
+          o6 = fmaf(oy, rk, -yl) * inv_dp_f;
+          o7 = fmaf(ovx, rk, -chf);
+          o8 = fmaf(ovy, rk, -shf);
           tt_f = fmaf(2.0f, kf, ttacc);  // sum of 1 + (dp - d)/dp
         } else {
           o5 = o6 = o7 = o8 = -1.f;
@@ -464,90 +506,103 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
 
       // -- UAV partners: prefilter on the NEW positions against (i) the communication radius widened by one move
       //    (a partner that moves after this UAV is tested at its old position, at most dt*v from the new one) and
-      //    (ii) the duplicate-tracking radius 2 dp
+      //    (ii) the duplicate-tracking radius 2 dp.  The own bit is always set (distance 0): the own slot is walked
+      //    like any other and the own contribution, known in closed form, is taken out afterwards.
       uint32_t ccE, ccO, cdE, cdO;
-      prefilter64<true>(S.pn2, xf, yf, Tf_hi, T2_hi, ccE, ccO, cdE, cdO);
-      ccE &= ~selfE; ccO &= ~selfO; cdE &= ~selfE; cdO &= ~selfO;  // never its own partner
-      // -- communication partners (uav.py:124-147): partner j < i already moved -> its new record, j > i -> its old one
+      prefilter64<true, (int)sizeof(SlotRec)>(S.slotn, xf, yf, Tf_hi, T2_hi, ccE, ccO, cdE, cdO);
+      const unsigned char *slot_new = reinterpret_cast<const unsigned char *>(S.slotn);
+      // -- communication partners (uav.py:124-147), two per slot.  Weights 1 / 0 from the upper guard; the largest
+      //    accepted squared distance tells afterwards whether an accepted pair sat inside the band (a partner of the
+      //    slot that the prefilter had excluded is either outside the upper guard or, by the guard's construction,
+      //    inside the band).
       {
-        uint64_t sd = 0, sh2 = 0;  // packed sums {dx, dy}, {cos, sin}
-        float sa = 0;
-        int cnt = 0;
-        constexpr uint32_t OLD_OFF = (uint32_t)(sizeof(float4) * 2 * N);
-#pragma unroll
-        for (int par = 0; par < 2; par++) {
-          uint32_t w = par ? ccO : ccE;
-          const uint32_t lt = par ? ltO : ltE;
-          const unsigned char *rec_new = reinterpret_cast<const unsigned char *>(&S.recn[par][0]);
+        uint64_t sx = 0, sy = 0, sc = 0, ss = 0, sa = 0, cn = 0;
+        float smax_c = 0.f;
+        uint32_t w = ccE | ccO;
 #pragma unroll 1
-          while (w) {
-            const int b = sf_msb(w);
-            const uint32_t bit = 1u << b;
-            w ^= bit;
-            const unsigned char *rp = ((bit & lt) ? rec_new : rec_new + OLD_OFF) + 64 * b;
-            const ulonglong2 r0 = *reinterpret_cast<const ulonglong2 *>(rp);  // {x, y}, {cos h, sin h}
-            const uint64_t d = f2_sub(r0.x, me2);
-            const uint64_t q = f2_mul(d, d);
-            const float s = f2_lo(q) + f2_hi(q);
-            if (s <= Tc_hi) {
-              const float aj = *reinterpret_cast<const float *>(rp + 16);
-              smax_c = fmaxf(smax_c, s);
-              sd = f2_add(sd, d);
-              sh2 = f2_add(sh2, r0.y);
-              sa += aj; cnt++;
-              if (AUX) { if (par) cmO |= bit; else cmE |= bit; }
-            }
-          }
+        while (w) {
+          const int b = sf_msb(w);
+          const uint32_t bit = 1u << b;
+          w ^= bit;
+          const unsigned char *rp = slot_new + ((b < ihx) ? 0u : OLD_OFF) + 48 * b;
+          const ulonglong2 p = *reinterpret_cast<const ulonglong2 *>(rp);         // {x0, x1}, {y0, y1}
+          const ulonglong2 hd = *reinterpret_cast<const ulonglong2 *>(rp + 16);   // {cos0, cos1}, {sin0, sin1}
+          const uint64_t aa = *reinterpret_cast<const uint64_t *>(rp + 32);       // {a0, a1}
+          const uint64_t dx = f2_sub(p.x, xf2), dy = f2_sub(p.y, yf2);
+          const uint64_t s2 = f2_fma(dx, dx, f2_mul(dy, dy));
+          const float s0 = f2_lo(s2), s1 = f2_hi(s2);
+          const bool h0 = s0 <= Tc_hi, h1 = s1 <= Tc_hi;
+          const uint64_t wh = pack2(h0 ? 1.0f : 0.0f, h1 ? 1.0f : 0.0f);
+          if (h0) smax_c = fmaxf(smax_c, s0);
+          if (h1) smax_c = fmaxf(smax_c, s1);
+          sx = f2_fma(wh, dx, sx); sy = f2_fma(wh, dy, sy);
+          sc = f2_fma(wh, hd.x, sc); ss = f2_fma(wh, hd.y, ss);
+          sa = f2_fma(wh, aa, sa);
+          cn = f2_add(cn, wh);
+          if (AUX) { if (h0) cmE |= bit; if (h1) cmO |= bit; }
         }
-        if (cnt) {
-          const float kf = (float)cnt, rk = sf_rcp(kf);
-          o0 = fmaf(f2_lo(sd), rk, -xl) * inv_dc_f;
-          o1 = fmaf(f2_hi(sd), rk, -yl) * inv_dc_f;
-          o2 = fmaf(f2_lo(sh2), rk, -chf);
-          o3 = fmaf(f2_hi(sh2), rk, -shf);
-          o4 = (sa - kf * (float)ai) * (rk * inv_na_f);
+        // own entry of the own slot: the record that was read there (new if this UAV sits in the odd place, else old)
+        // (the own entry also went into smax_c: its distance is 0 or one move, far from the band unless dt*v ~ dc,
+        // and then the exact path takes over -- slower, still right)
+        float own_w, own_dx, own_dy, own_c, own_s, own_a;
+        {
+          const float *r = reinterpret_cast<const float *>(slot_new + (ic ? 0u : OLD_OFF) + 48 * ih) + ic;
+          own_dx = r[0] - xf; own_dy = r[2] - yf; own_c = r[4]; own_s = r[6]; own_a = r[8];
+          const float s_own = fmaf(own_dx, own_dx, own_dy * own_dy);
+          own_w = sf_le(s_own, Tc_hi);
+        }
+        const float cntf = (f2_lo(cn) + f2_hi(cn)) - own_w;
+        amb |= smax_c > Tc_lo;
+        if (AUX) { if (ic) cmO &= ~(1u << ih); else cmE &= ~(1u << ih); }
+        if (cntf > 0.5f) {
+          const float rk = sf_rcp(cntf);
+          o0 = fmaf((f2_lo(sx) + f2_hi(sx)) - own_w * own_dx, rk, -xl) * inv_dc_f;
+          o1 = fmaf((f2_lo(sy) + f2_hi(sy)) - own_w * own_dy, rk, -yl) * inv_dc_f;
+          o2 = fmaf((f2_lo(sc) + f2_hi(sc)) - own_w * own_c, rk, -chf);
+          o3 = fmaf((f2_lo(ss) + f2_hi(ss)) - own_w * own_s, rk, -shf);
+          o4 = (((f2_lo(sa) + f2_hi(sa)) - own_w * own_a) - cntf * (float)ai) * (rk * inv_na_f);
         } else {
           o0 = o1 = o2 = o3 = o4 = -1.f;
         }
       }
-      // -- duplicate-tracking punishment (uav.py:214-229) and the neighbour set (uav.py:305), all at NEW positions
+      // -- duplicate-tracking punishment (uav.py:214-229) and the neighbour set (uav.py:305), all at NEW positions.
+      //    One partner per trip: with two MUFU per partner and two radii to flag, a slot trip cost twice a single one.
       {
-        float dup = 0;
+        float dup = 0, smax_d = 0.f, smax_n = 0.f;
+        cdE &= ~(ic ? 0u : (1u << ih)); cdO &= ~(ic ? (1u << ih) : 0u);  // never its own partner
         if (AUX) { dpE = cdE; dpO = cdO; }
 #pragma unroll
         for (int par = 0; par < 2; par++) {
           uint32_t w = par ? cdO : cdE, nbits = 0;
-          const unsigned char *rec_new = reinterpret_cast<const unsigned char *>(&S.recn[par][0]);
+          const unsigned char *rec = slot_new + 4 * par;
 #pragma unroll 1
           while (w) {
             const int b = sf_msb(w);
             const uint32_t bit = 1u << b;
             w ^= bit;
-            const uint64_t d = f2_sub(*reinterpret_cast<const uint64_t *>(rec_new + 64 * b), me2);
-            const uint64_t q = f2_mul(d, d);
-            const float s = f2_lo(q) + f2_hi(q);
-            smax_d = fmaxf(smax_d, s);
+            const float *r = reinterpret_cast<const float *>(rec + 48 * b);
+            const float dx = r[0] - xf, dy = r[2] - yf;
+            const float s = fmaf(dx, dx, dy * dy);
+            smax_d = fmaxf(smax_d, s);  // every candidate is accepted
             dup += fast_ex2f(fmaf(fast_sqrtf(s), k_ex1, k_ex0));  // exp((2dp - d)/(2dp))
-            if (s <= Tp_hi) {
-              nbits |= bit;
-              smax_n = fmaxf(smax_n, s);
-            }
+            if (s <= Tp_hi) { nbits |= bit; smax_n = fmaxf(smax_n, s); }
           }
           if (par) nbO = nbits; else nbE = nbits;
         }
+        amb |= (smax_d > T2_lo) || (smax_n > Tp_lo);
         dup_f = -0.5f * dup;
       }
-      exact = (smax_t > Tp_lo) || (smax_c > Tc_lo) || (smax_d > T2_lo) || (smax_n > Tp_lo);
+      exact = amb;
     }
     if (exact) {
       const ExactK XK = {P.s_dp_le, P.s_dp_lt, P.s_2dp_le, P.s_dc_le, P.dp, P.dc, P.two_dp, P.na};
       const MaskPtrs MP = {B.obs_mask, B.comm_mask, B.nbr_mask, B.dup_mask, B.cover_mask};
-      fast_agent_exact<N, M, AUX>(XK, MP, S, t, mrow_t, mrow_u);
-      const float *ob = S.obs + t * 12;
-      o0 = ob[0]; o1 = ob[1]; o2 = ob[2]; o3 = ob[3]; o4 = ob[4]; o5 = ob[5]; o6 = ob[6]; o7 = ob[7]; o8 = ob[8];
-      tt_f = ob[9]; dup_f = ob[10];
-      nbE = __float_as_uint(S.rew[0][t]); nbO = __float_as_uint(S.rew[1][t]);
-      cvE = __float_as_uint(S.rew[2][t]); cvO = __float_as_uint(S.rew[3][t]);
+      FastAgent X;
+      fast_agent_exact<N, M, AUX>(XK, MP, S, t, mrow_t, mrow_u, &X);
+      o0 = X.ob[0]; o1 = X.ob[1]; o2 = X.ob[2]; o3 = X.ob[3]; o4 = X.ob[4];
+      o5 = X.ob[5]; o6 = X.ob[6]; o7 = X.ob[7]; o8 = X.ob[8];
+      tt_f = X.tt; dup_f = X.dup;
+      nbE = X.nb[0]; nbO = X.nb[1]; cvE = X.cov[0]; cvO = X.cov[1];
     } else if (AUX && B.obs_mask) {
       for (int j = 0; j < 64; j++) {
         const int b = j >> 1;
@@ -570,75 +625,79 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
       if (lane == 0) { S.cover[warp][0] = c0; S.cover[warp][1] = c1; }
     }
 
-    double raw, ttn, bpn, dupn;
+    // The terms below only feed fp32 outputs (and fp64 statistics of those outputs): evaluated in fp32.  The one
+    // decision among them, inside / outside the map (uav.py:239), stays in fp64.
+    float raw, ttn, bpn, dupn;
     {
-      float *ob = S.obs + t * 12;
-      reinterpret_cast<float4 *>(ob)[0] = make_float4(o0, o1, o2, o3);
-      reinterpret_cast<float4 *>(ob)[1] = make_float4(o4, o5, o6, o7);
-      reinterpret_cast<float4 *>(ob)[2] = make_float4(o8, (float)(xi * P.inv_dc), (float)(yi * P.inv_dc), (float)ai * inv_na_f);
       // boundary punishment (uav.py:231-250)
-      const double dbdr = fmin(fmin(xi - 0, P.x_max - xi), fmin(yi - 0, P.y_max - yi));
-      double bp;
-      if (0 <= xi && xi <= P.x_max && 0 <= yi && yi <= P.y_max)
-        bp = (dbdr < P.dp) ? (-0.5 * (P.dp - dbdr) * P.inv_dp) : 0.0;
-      else
-        bp = -0.5;
+      const bool inside = 0 <= xi && xi <= P.x_max && 0 <= yi && yi <= P.y_max;
+      const float dbdr = (float)fmin(fmin(xi - 0, P.x_max - xi), fmin(yi - 0, P.y_max - yi));
+      const float dp_f = (float)P.dp;
+      const float bp = inside ? ((dbdr < dp_f) ? (-0.5f * (dp_f - dbdr) * inv_dp_f) : 0.0f) : -0.5f;
       // normalise + weights (environment.py:206-220)
-      ttn = fmin(fmax((double)tt_f, 0.0), P.tt_hi) * P.inv_tt_hi;
-      dupn = (fmin(fmax((double)dup_f, P.dup_lo), 0.0) - P.dup_lo) * P.inv_dup_span - 1.0;
-      bpn = (fmin(fmax(bp, -0.5), 0.0) + 0.5) * 2.0 - 1.0;
-      raw = P.alpha * ttn + P.beta * bpn + P.gamma * dupn;
+      const float dup_lo = (float)P.dup_lo;
+      ttn = fminf(fmaxf(tt_f, 0.0f), (float)P.tt_hi) * (float)P.inv_tt_hi;
+      dupn = (fminf(fmaxf(dup_f, dup_lo), 0.0f) - dup_lo) * (float)P.inv_dup_span - 1.0f;
+      bpn = (fminf(fmaxf(bp, -0.5f), 0.0f) + 0.5f) * 2.0f - 1.0f;
+      raw = fmaf((float)P.alpha, ttn, fmaf((float)P.beta, bpn, (float)P.gamma * dupn));
       S.raw[t] = raw;
     }
-    __syncthreads();
+    __syncthreads();  // every walk is over: the slot areas become the output staging
 
     // ---- phase 2: cooperative reward (environment.py:222-227), coverage count, outputs ----
     {
-      double r;
+      float *ob = s_obs + t * 12;
+      reinterpret_cast<float4 *>(ob)[0] = make_float4(o0, o1, o2, o3);
+      reinterpret_cast<float4 *>(ob)[1] = make_float4(o4, o5, o6, o7);
+      reinterpret_cast<float4 *>(ob)[2] = make_float4(o8, (float)(xi * P.inv_dc), (float)(yi * P.inv_dc), (float)ai * inv_na_f);
+      float r;
       const int64_t gi = e * N + t;
       if (mode == UAVSIM_MODE_SELF || coop == 0.0) {
         r = raw;  // uav.py:271-272 / :300-301
       } else if (mode == UAVSIM_MODE_MEAN) {
         // uav.py:293-310 -- the conditional expression covers the whole sum: no neighbour -> 0
-        double s = 0;
+        float s = 0;
         const int cnt = __popc(nbE) + __popc(nbO);
 #pragma unroll
         for (int par = 0; par < 2; par++) {
           uint32_t w = par ? nbO : nbE;
           while (w) { const int b = sf_msb(w); w ^= 1u << b; s += S.raw[2 * b + par]; }
         }
-        r = cnt ? ((1 - coop) * raw + coop * s / (double)cnt) : 0.0;
+        const float cf = (float)coop;
+        r = cnt ? fmaf(1.0f - cf, raw, cf * s * sf_rcp((float)cnt)) : 0.0f;
       } else {
-        r = 0.0;  // finished by the PMI kernel
-        B.raw[gi] = raw;
+        r = 0.0f;  // finished by the PMI kernel
+        B.raw[gi] = (double)raw;
         B.nbr_bits[gi * 2] = sf_interleave(nbE, nbO);
         B.nbr_bits[gi * 2 + 1] = 0;
       }
-      r = fmin(fmax(r, -1.0), 1.0);  // clip_and_normalize(reward, -1, 1) is a plain clip
-      S.rew[0][t] = (float)r;
-      S.rew[1][t] = (float)ttn;
-      S.rew[2][t] = (float)bpn;
-      S.rew[3][t] = (float)dupn;
-      if (!pmi_pending) st_r += r;
-      st_tt += ttn; st_bp += bpn; st_dup += dupn;
+      r = fminf(fmaxf(r, -1.0f), 1.0f);  // clip_and_normalize(reward, -1, 1) is a plain clip
+      s_rew[t] = r;
+      s_rew[N + t] = ttn;
+      s_rew[2 * N + t] = bpn;
+      s_rew[3 * N + t] = dupn;
+      if (!pmi_pending) st_r += (double)r;
+      st_tt += (double)ttn; st_bp += (double)bpn; st_dup += (double)dupn;
       if (AUX && B.tracker_cnt) B.tracker_cnt[e * M + t] = S.tcnt[t];
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk copies
     __syncthreads();
     if (warp == 0) {
-      sf_bulk_s2g(lead, B.ux + e * N, sf_smem(S.oux), N * 8);
-      sf_bulk_s2g(lead, B.uy + e * N, sf_smem(S.ouy), N * 8);
-      sf_bulk_s2g(lead, B.uh + e * N, sf_smem(S.ouh), N * 8);
-      sf_bulk_s2g(lead, B.ua + e * N, sf_smem(S.oua), N * 4);
-      sf_bulk_s2g(lead, B.tx + e * M, sf_smem(S.otx), M * 8);
-      sf_bulk_s2g(lead, B.ty + e * M, sf_smem(S.oty), M * 8);
-      sf_bulk_s2g(lead, B.th + e * M, sf_smem(S.oth), M * 8);
-      sf_bulk_s2g(lead, B.obs + e * N * 12, sf_smem(S.obs), N * 48);
-      if (!pmi_pending) sf_bulk_s2g(lead, B.rew4 + e * N, sf_smem(S.rew[0]), N * 4);
-      sf_bulk_s2g(lead, B.rew4 + plane + e * N, sf_smem(S.rew[1]), N * 4);
-      sf_bulk_s2g(lead, B.rew4 + 2 * plane + e * N, sf_smem(S.rew[2]), N * 4);
-      sf_bulk_s2g(lead, B.rew4 + 3 * plane + e * N, sf_smem(S.rew[3]), N * 4);
-      if (lead) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      if (elect_one()) {
+        sf_bulk_s2g(B.ux + e * N, sf_smem(S.oux), N * 8);
+        sf_bulk_s2g(B.uy + e * N, sf_smem(S.ouy), N * 8);
+        sf_bulk_s2g(B.uh + e * N, sf_smem(S.ouh), N * 8);
+        sf_bulk_s2g(B.ua + e * N, sf_smem(S.oua), N * 4);
+        sf_bulk_s2g(B.tx + e * M, sf_smem(S.otx), M * 8);
+        sf_bulk_s2g(B.ty + e * M, sf_smem(S.oty), M * 8);
+        sf_bulk_s2g(B.th + e * M, sf_smem(S.oth), M * 8);
+        sf_bulk_s2g(B.obs + e * N * 12, sf_smem(s_obs), N * 48);
+        if (!pmi_pending) sf_bulk_s2g(B.rew4 + e * N, sf_smem(s_rew), N * 4);
+        sf_bulk_s2g(B.rew4 + plane + e * N, sf_smem(s_rew + N), N * 4);
+        sf_bulk_s2g(B.rew4 + 2 * plane + e * N, sf_smem(s_rew + 2 * N), N * 4);
+        sf_bulk_s2g(B.rew4 + 3 * plane + e * N, sf_smem(s_rew + 3 * N), N * 4);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
     }
     if (t == 0) {
       const int c = __popc(S.cover[0][0] | S.cover[1][0]) + __popc(S.cover[0][1] | S.cover[1][1]);
@@ -649,8 +708,11 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
       st_envs += 1.0;
     }
   }
-  if (lead) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // outputs complete before the CTA retires
+  __syncwarp();
+  if (warp == 0) {
+    if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // outputs complete before the CTA retires
+  }
   __syncthreads();
-  block_stats_commit(reinterpret_cast<double *>(S.obs), stats_partial + (size_t)blockIdx.x * STAT_W, st_r, st_tt, st_bp,
+  block_stats_commit(reinterpret_cast<double *>(S.ux), stats_partial + (size_t)blockIdx.x * STAT_W, st_r, st_tt, st_bp,
                      st_dup, st_cov, st_cmax, st_envs, FAST_NT);
 }
