@@ -54,6 +54,10 @@ struct KParams {
   // environment).  s_f <= t2_dn - g: certainly inside; s_f > t2_up + g: certainly outside; between: decided in fp64.
   GuardK g_dp, g_2dp, g_dc, g_pf;
   float r_fast;   // the fast kernel serves environments whose entities stay within this distance of the map centre
+  // fp32 copies of the constants the fast kernel's fp32 output arithmetic uses (no per-iteration conversions)
+  float dp_f, inv_dp_f, inv_dc_f, inv_na_f, tt_hi_f, inv_tt_hi_f, dup_lo_f, inv_dup_span_f, alpha_f, beta_f, gamma_f;
+  float k_ex1_f, tv_over_uv_f, cx_f, cy_f;
+  const double *sincos_tab;  // [FM_TAB_SIZE][2] sine / cosine of k pi/32 (fast_math.cuh), device memory
 };
 
 struct PmiDev {
@@ -92,6 +96,7 @@ struct uavsim {
   size_t smem_fast[2];
   int fast_grid_max[2];
   ActEntry *d_act;          // [na] per action: dt * rate (fp64), cos / sin of it (fp32)
+  double *d_sctab;          // sine / cosine table of the fast kernel's heading routine
   // pmi
   bool has_pmi;
   PmiDev pmi;

@@ -92,3 +92,51 @@ FM_HD void fm_sincos_small(double h, double *sn, double *cs) {
   *sn = (k & 2) ? -s_ : s_;
   *cs = ((k + 1) & 2) ? -c_ : c_;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Table variant for |h| <= pi + a little (|h| < 3.3): h = k * pi/32 + r with |r| <= pi/64, sine and cosine of the
+// 69 grid angles from a table, of r from two short series (r^9 / 9! < 5e-18), combined as
+//   sin h = S_k + (S_k (cos r - 1) + C_k sin r),   cos h = C_k + (C_k (cos r - 1) - S_k sin r)
+// so the table value enters unscaled and only a term <= 0.05 is computed: max error ~1 ulp (checked on the host by
+// tests/test_fast_math.py).  26 fp64 instructions instead of ~70 for the polynomial-only routine above.
+// ------------------------------------------------------------------------------------------------
+#define FM_TAB_HALF 34                       // k = -34 .. 34 (|h| < 3.3 gives |k| <= 34)
+#define FM_TAB_SIZE (2 * FM_TAB_HALF + 1)    // entries {sin, cos}
+
+static inline void fm_fill_table(double *tab /* [FM_TAB_SIZE][2] */) {
+  for (int k = -FM_TAB_HALF; k <= FM_TAB_HALF; k++) {
+    // k * pi/32 evaluated exactly enough for a correctly rounded libm result: pi/32 = hi + lo
+    const long double a = (long double)k * (3.14159265358979323846264338327950288L / 32.0L);
+    tab[2 * (k + FM_TAB_HALF)] = (double)sinl(a);
+    tab[2 * (k + FM_TAB_HALF) + 1] = (double)cosl(a);
+  }
+}
+
+FM_HD void fm_sincos_tab(double h, const double *tab, double *sn, double *cs) {
+  const double SHIFT = 6755399441055744.0;
+  const double ks = fma(h, 1.01859163578813021189e+01 /* 32/pi */, SHIFT);
+#ifdef __CUDA_ARCH__
+  const int k = __double2loint(ks);
+#else
+  uint64_t kb;
+  memcpy(&kb, &ks, 8);
+  const int k = (int)(uint32_t)kb;
+#endif
+  const double kd = ks - SHIFT;
+  // pi/32 = 9.81747704246810387019e-02: first 33 bits, then the rest (k <= 33: the first product is exact)
+  const double r0 = fma(-kd, 9.81747704208828508854e-02, h);
+  const double r = fma(-kd, 3.79818781656637015582e-12, r0);
+  const double z = r * r;
+  // sin r = r + r z (-1/6 + z (1/120 + z (-1/5040))),  cos r - 1 = z (-1/2 + z (1/24 + z (-1/720 + z / 40320)))
+  const double ps = fma(z, fma(z, -1.98412698412698412526e-04, 8.33333333333333321769e-03), -1.66666666666666657415e-01);
+  const double sr = fma(r * z, ps, r);
+  const double cm = z * fma(z, fma(z, fma(z, 2.48015873015873015658e-05, -1.38888888888888894189e-03), 4.16666666666666643537e-02), -0.5);
+#ifdef __CUDA_ARCH__
+  const double2 sc = __ldg(reinterpret_cast<const double2 *>(tab) + (k + FM_TAB_HALF));  // one 128-bit load, L1 resident
+  const double S = sc.x, C = sc.y;
+#else
+  const double S = tab[2 * (k + FM_TAB_HALF)], C = tab[2 * (k + FM_TAB_HALF) + 1];
+#endif
+  *sn = S + fma(S, cm, C * sr);
+  *cs = C + fma(C, cm, -(S * sr));
+}

@@ -295,10 +295,10 @@ __device__ __noinline__ void fast_agent_exact(const ExactK P, const MaskPtrs B, 
 
 // sin / cos of a heading: the wrapped range takes the inline routine, anything else the library one (whose pointer
 // arguments stay inside the cold branch)
-__device__ __forceinline__ void heading_sincos(double h, double &s, double &c) {
-  if (fabs(h) < 4.0) {
+__device__ __forceinline__ void heading_sincos(double h, const double *tab, double &s, double &c) {
+  if (fabs(h) < 3.3) {
     double s1, c1;
-    fm_sincos_small(h, &s1, &c1);
+    fm_sincos_tab(h, tab, &s1, &c1);
     s = s1; c = c1;
   } else {
     double s2, c2;
@@ -354,8 +354,8 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
   }
 
   const int64_t plane = P.E * N;
-  const float inv_dp_f = (float)P.inv_dp, inv_dc_f = (float)P.inv_dc, inv_na_f = (float)P.inv_na;
-  const float k_ex0 = 1.4426950408889634f, k_ex1 = (float)(-1.4426950408889634 / P.two_dp);
+  const float inv_dp_f = P.inv_dp_f, inv_dc_f = P.inv_dc_f, inv_na_f = P.inv_na_f;
+  const float k_ex0 = 1.4426950408889634f, k_ex1 = P.k_ex1_f;
   double st_r = 0, st_tt = 0, st_bp = 0, st_dup = 0, st_cov = 0, st_envs = 0;
   int st_cmax = 0;
   uint32_t parity = 0;
@@ -380,7 +380,7 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
     {
       double x = S.tx[t], y = S.ty[t], h = S.th[t];
       double sh, ch;
-      heading_sincos(h, sh, ch);
+      heading_sincos(h, P.sincos_tab, sh, ch);
       x += P.dtv_t * ch;
       y += P.dtv_t * sh;
       // reflection (target.py:52-58); cos(-h) = cos h, sin(-h) = -sin h, cos(+-pi - h) = -cos h, sin(+-pi - h) = sin h
@@ -390,7 +390,7 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
       const float txf = (float)(x - P.cx), tyf = (float)(y - P.cy);
       float *ts = reinterpret_cast<float *>(&S.tslot[ih]) + ic;
       ts[0] = txf; ts[2] = tyf;
-      ts[4] = (float)(ch * P.tv_over_uv); ts[6] = (float)(sh * P.tv_over_uv);
+      ts[4] = (float)ch * P.tv_over_uv_f; ts[6] = (float)sh * P.tv_over_uv_f;
       rabs = fmaxf(fabsf(txf), fabsf(tyf));
       if (AUX) S.tcnt[t] = 0;
     }
@@ -402,7 +402,7 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
       double x = S.ux[t], y = S.uy[t], h = S.uh[t];
       const int a_old = S.ua[t], act = S.act[t];
       double sh, ch;
-      heading_sincos(h, sh, ch);
+      heading_sincos(h, P.sincos_tab, sh, ch);
       const float cof = (float)ch, sof = (float)sh;
       const float xof = (float)(x - P.cx), yof = (float)(y - P.cy);
       S.xo[t] = x; S.yo[t] = y;
@@ -629,17 +629,18 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
     // decision among them, inside / outside the map (uav.py:239), stays in fp64.
     float raw, ttn, bpn, dupn;
     {
-      // boundary punishment (uav.py:231-250)
-      const bool inside = 0 <= xi && xi <= P.x_max && 0 <= yi && yi <= P.y_max;
-      const float dbdr = (float)fmin(fmin(xi - 0, P.x_max - xi), fmin(yi - 0, P.y_max - yi));
-      const float dp_f = (float)P.dp;
-      const float bp = inside ? ((dbdr < dp_f) ? (-0.5f * (dp_f - dbdr) * inv_dp_f) : 0.0f) : -0.5f;
+      // boundary punishment (uav.py:231-250).  Distance to the nearest wall from the centred fp32 coordinates; the
+      // inside / outside decision (closed interval, uav.py:239) falls back to fp64 within a millimetre of a wall.
+      // (The value is continuous across the wall, -1/2 on both sides; the decision only has to be consistent.)
+      const float dbdr = fminf(P.cx_f - fabsf(xf), P.cy_f - fabsf(yf));
+      bool inside = dbdr > 0.f;
+      if (fabsf(dbdr) < 1e-3f) inside = 0 <= xi && xi <= P.x_max && 0 <= yi && yi <= P.y_max;
+      const float bp = inside ? ((dbdr < P.dp_f) ? (-0.5f * (P.dp_f - dbdr) * inv_dp_f) : 0.0f) : -0.5f;
       // normalise + weights (environment.py:206-220)
-      const float dup_lo = (float)P.dup_lo;
-      ttn = fminf(fmaxf(tt_f, 0.0f), (float)P.tt_hi) * (float)P.inv_tt_hi;
-      dupn = (fminf(fmaxf(dup_f, dup_lo), 0.0f) - dup_lo) * (float)P.inv_dup_span - 1.0f;
+      ttn = fminf(fmaxf(tt_f, 0.0f), P.tt_hi_f) * P.inv_tt_hi_f;
+      dupn = (fminf(fmaxf(dup_f, P.dup_lo_f), 0.0f) - P.dup_lo_f) * P.inv_dup_span_f - 1.0f;
       bpn = (fminf(fmaxf(bp, -0.5f), 0.0f) + 0.5f) * 2.0f - 1.0f;
-      raw = fmaf((float)P.alpha, ttn, fmaf((float)P.beta, bpn, (float)P.gamma * dupn));
+      raw = fmaf(P.alpha_f, ttn, fmaf(P.beta_f, bpn, P.gamma_f * dupn));
       S.raw[t] = raw;
     }
     __syncthreads();  // every walk is over: the slot areas become the output staging

@@ -158,6 +158,18 @@ extern "C" int uavsim_create(const UavSimParams *p, int64_t n_envs, int64_t env_
     if (rf > k.rmax) rf = k.rmax;
     k.r_fast = (float)rf;
   }
+  k.dp_f = (float)p->dp; k.inv_dp_f = (float)k.inv_dp; k.inv_dc_f = (float)k.inv_dc; k.inv_na_f = (float)k.inv_na;
+  k.tt_hi_f = (float)k.tt_hi; k.inv_tt_hi_f = (float)k.inv_tt_hi; k.dup_lo_f = (float)k.dup_lo; k.inv_dup_span_f = (float)k.inv_dup_span;
+  k.alpha_f = (float)k.alpha; k.beta_f = (float)k.beta; k.gamma_f = (float)k.gamma;
+  k.k_ex1_f = (float)(-1.4426950408889634 / k.two_dp); k.tv_over_uv_f = (float)k.tv_over_uv;
+  k.cx_f = (float)k.cx; k.cy_f = (float)k.cy;
+  {
+    double tab[FM_TAB_SIZE * 2];
+    fm_fill_table(tab);
+    CUDA_TRY(cudaMalloc(&h->d_sctab, sizeof(tab)));
+    CUDA_TRY(cudaMemcpy(h->d_sctab, tab, sizeof(tab), cudaMemcpyHostToDevice));
+    k.sincos_tab = h->d_sctab;
+  }
 
   // per action: dt * discrete_action(a) (src/agent/uav.py:73-81, :96) in the reference's evaluation order,
   // plus its cosine / sine for the angle-addition update of the observation heading terms
@@ -245,7 +257,7 @@ extern "C" int uavsim_create(const UavSimParams *p, int64_t n_envs, int64_t env_
 extern "C" int uavsim_destroy(uavsim_t *h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
-  cudaFree(h->d_dth); cudaFree(h->d_act); cudaFree(h->d_stats); cudaFree(h->d_stats8); cudaFreeHost(h->h_stats8);
+  cudaFree(h->d_dth); cudaFree(h->d_act); cudaFree(h->d_sctab); cudaFree(h->d_stats); cudaFree(h->d_stats8); cudaFreeHost(h->h_stats8);
   cudaFree(h->d_pmi_blob); cudaFree(h->d_tc_tiles);
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_comp) cudaStreamDestroy(h->s_comp);
@@ -279,6 +291,7 @@ extern "C" int uavsim_set_reward_weights(uavsim_t *h, double alpha, double beta,
   h->hp.alpha = h->kp.alpha = alpha;
   h->hp.beta = h->kp.beta = beta;
   h->hp.gamma = h->kp.gamma = gamma;
+  h->kp.alpha_f = (float)alpha; h->kp.beta_f = (float)beta; h->kp.gamma_f = (float)gamma;
   return 0;
 }
 
