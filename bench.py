@@ -45,6 +45,67 @@ def alg_bytes_per_env_step(n, m):
     return 124 * n + 48 * m + 4
 
 
+def workload_config(name, E):
+    """The `config` object of the JSON line: identical in the native and the reference arm."""
+    n, m, _, method, desc = WORKLOADS[name]
+    return {"workload": name, "description": desc, "n_uav": n, "m_targets": m, "envs_per_gpu": E, "method": method}
+
+
+def python_reference_rate(budget_s=6.0):
+    """The reference's own Python `Environment.step` (baseline/_ref/src, unmodified) timed on this box: one process, one
+    environment -- the way the reference runs (src/environment.py:120) -- for 64x64 and 10x10, MAAC-G reward, random
+    actions.  A few steps each (bounded by `budget_s`); None when the copy of the reference is absent."""
+    try:
+        import random
+        import numpy as np
+        import torch
+        import baseline
+        if not baseline.available():
+            return None
+        ref = baseline.import_reference()
+        torch.set_num_threads(1)
+        out = {"source": "baseline/_ref/src Environment.step (unmodified reference), 1 process, 1 thread", "cases": {}}
+        for n, m in ((64, 64), (10, 10)):
+            cfg = baseline.load_yaml_config("MAAC-G")
+            cfg["environment"].update(n_uav=n, m_targets=m)
+            random.seed(0)
+            env = ref.environment.Environment(n_uav=n, m_targets=m, x_max=2000, y_max=2000, na=12)
+            env.reset(cfg)
+            rng = np.random.RandomState(0)
+            acts = [[int(a) for a in rng.randint(0, 12, size=n)] for _ in range(400)]
+            env.step(cfg, None, acts[0])
+            t0, k = time.perf_counter(), 0
+            while k < 399 and time.perf_counter() - t0 < budget_s / 2:
+                env.step(cfg, None, acts[k + 1])
+                k += 1
+            dt = time.perf_counter() - t0
+            out["cases"]["%dx%d" % (n, m)] = {"value": n * k / dt, "unit": "agent-steps/s", "steps": k, "seconds": dt}
+        return out
+    except Exception as exc:  # noqa: BLE001  (a reported baseline must never take the GPU line down)
+        return {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
+
+
+def link_probe(torch, device, h2d_bytes, d2h_bytes, reps=5):
+    """Bare pinned-memory copies of the e2e step's byte counts (no kernels): what the host link gives this process."""
+    h_in = torch.empty(max(h2d_bytes, 1), dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(max(d2h_bytes, 1), dtype=torch.uint8).pin_memory()
+    d_in, d_out = torch.empty_like(h_in, device=device), torch.empty_like(h_out, device=device)
+    s_in, s_out = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    for _ in range(2):
+        d_in.copy_(h_in, non_blocking=True)
+        h_out.copy_(d_out, non_blocking=True)
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    for _ in range(reps):  # both directions at once, like the pipelined step
+        with torch.cuda.stream(s_in):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            h_out.copy_(d_out, non_blocking=True)
+    torch.cuda.synchronize(device)
+    dt = (time.perf_counter() - t0) / reps
+    return {"ms": dt * 1e3, "gbs": (h2d_bytes + d2h_bytes) / dt / 1e9}
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -189,26 +250,26 @@ def run_reference_arm(args, rank, world):
             one /= 2
     Es = min(Es, E)
     st = {k: np.ascontiguousarray(v) for k, v in reset_reference(0, Es, n, m, 12, 2000, 2000).items()}
-    for _ in range(args.warmup):
-        orc.step_batch(P, mode, float(cfg["cooperative"]), pmi, st, rng.randint(0, 12, size=(Es, n)).astype(np.int32),
-                       nthreads=threads, want_tracker=False)
+    # random-policy actions drawn BEFORE the timed loop, one [Es,n] array per step -- exactly what the native arm does
+    # with its resident action bank: both arms time the environment step and nothing else
+    bank = [rng.randint(0, 12, size=(Es, n)).astype(np.int32) for _ in range(args.warmup + args.steps)]
+    for i in range(args.warmup):
+        orc.step_batch(P, mode, float(cfg["cooperative"]), pmi, st, bank[i], nthreads=threads, want_tracker=False)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        orc.step_batch(P, mode, float(cfg["cooperative"]), pmi, st, rng.randint(0, 12, size=(Es, n)).astype(np.int32),
-                       nthreads=threads, want_tracker=False)
+    for i in range(args.steps):
+        orc.step_batch(P, mode, float(cfg["cooperative"]), pmi, st, bank[args.warmup + i], nthreads=threads, want_tracker=False)
     dt = time.perf_counter() - t0
     value = Es * n * args.steps / dt
     sample = "%d envs (sample of %d x %d GPUs) x %d steps of %dx%d %s" % (Es, E, args.gpus, args.steps, n, m, method)
     out = {"impl": "reference", "metric": "agent-steps/s", "value": value, "unit": "agent-steps/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": args.workload, "description": desc, "n_uav": n, "m_targets": m,
-                      "envs_per_gpu": E, "method": method},
+           "config": workload_config(args.workload, E),
            "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": threads, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0,
            "note": "CPU oracle (C restatement of the reference's Python loops, pinned to the reference by tests/golden); "
-                   "the Python reference itself measured 3.7e3 agent-steps/s/core on this scenario (SURVEY.md section 6)"}
+                   "the Python reference itself is timed by the native arm (cpu_baseline.python_reference)"}
     print(json.dumps(out), flush=True)
 
 
@@ -292,6 +353,24 @@ def measure_workload(torch, dist, env_cls, args, name, rank, world, device, step
                           "ms_per_step": ms_loop / steps, "api": "uavsim_run_random_policy (actions drawn on the device)"}
 
     if with_e2e:
+        # ms per step over one whole 200-step episode (the timed window above sits where the driver's --steps /
+        # --warmup put it: right after the reset, when the swarm is densest)
+        env.reset(cfg)
+        NBe = min(EPISODE, NB)
+        barrier()
+        ev0.record(torch.cuda.current_stream(device))
+        for i in range(EPISODE):
+            env.bind_actions(bank[i % NBe])
+            env.step_device(cfg, pmi)
+        ev1.record(torch.cuda.current_stream(device))
+        barrier()
+        ms_ep = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms_ep], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_ep = float(t.item())
+        res["episode"] = {"steps": EPISODE, "ms_per_step": ms_ep / EPISODE, "value": E * world * n * EPISODE / (ms_ep * 1e-3),
+                          "unit": "agent-steps/s", "actions": "bank of %d pre-drawn steps" % NBe}
         NH = min(NB, e2e_steps + 2)
         h_act = torch.empty((NH, E, n), dtype=torch.int32).pin_memory()
         h_act.copy_(bank[:NH].cpu())
@@ -315,6 +394,18 @@ def measure_workload(torch, dist, env_cls, args, name, rank, world, device, step
                       "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3, "chunks": args.chunks,
                       "api": "BatchedEnvironment.step_host -> uavsim_step_host (pinned host buffers)"}
         res["checksum"] = float(h_rew[0].double().sum())
+        try:
+            lp = link_probe(torch, device, res["e2e"]["h2d_bytes_per_step"], res["e2e"]["d2h_bytes_per_step"])
+            if world > 1:
+                t = torch.tensor([lp["ms"]], dtype=torch.float64, device=device)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                lp["ms"] = float(t.item())
+                lp["gbs"] = (res["e2e"]["h2d_bytes_per_step"] + res["e2e"]["d2h_bytes_per_step"]) / (lp["ms"] * 1e-3) / 1e9
+            res["e2e"]["link_ms_per_step"] = lp["ms"]
+            res["e2e"]["link_gbs"] = lp["gbs"]     # per GPU, all ranks copying at the same time
+            res["e2e"]["link_frac"] = lp["ms"] / res["e2e"]["ms_per_step"]  # share of the e2e step the bare copies take
+        except Exception as exc:  # noqa: BLE001
+            res["e2e"]["link_probe_error"] = str(exc)[:120]
     # the one collective of the path: episode statistics (<= 8 doubles), outside the timed region
     from marl_uavs_targets_tracking_b200 import reduce_episode_stats
     res["episode_stats"] = reduce_episode_stats(env.episode_stats(), device=device)
@@ -439,22 +530,25 @@ def main():
         out = {"metric": "agent-steps/s", "value": main_res["value"], "unit": "agent-steps/s", "n_gpus": world,
                "steps": main_res["steps"], "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": {"workload": args.workload, "description": main_res["desc"], "n_uav": n, "m_targets": m,
-                          "envs_per_gpu": E, "method": main_res["method"], "episode_len": EPISODE,
+               "config": workload_config(args.workload, E),
+               "timing": {"episode_len": EPISODE, "window": "steps %d..%d after a reset" % (args.warmup, args.warmup + main_res["steps"] - 1),
                           "l2": "per-step working set %.0f MB > 126 MB L2 (inputs larger than L2, no flush needed)" % (bytes_per_launch / 1e6)},
                "clocks": main_res["clocks"], "e2e": main_res["e2e"], "gpu_launches": main_res["launches"],
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": traffic, "peak_source": peak_src, "kernel": "uavsim_step_kernel",
+                            "traffic": traffic,
+                            "traffic_source": "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full "
+                                              "capture of this kernel (committed with the round; not measured by this run)",
+                            "peak_source": peak_src, "kernel": "uavsim_step_fast_kernel<64,64>" if (n, m) == (64, 64) else "uavsim_step_kernel",
                             "bytes_per_launch": bytes_per_launch,
                             "bytes_per_agent_step": alg_bytes_per_env_step(n, m) / n},
-               "device_loop": main_res["device_loop"],
+               "device_loop": main_res["device_loop"], "episode": main_res.get("episode"),
                "episode_stats": main_res["episode_stats"], "other_workloads": extras}
         if main_res.get("trace"):
             out["ms_per_step_trace"] = {"every": args.trace_every, "ms": main_res["trace"]}
         if affinity:
             os.sched_setaffinity(0, affinity[0])
         out["host_affinity"] = None if not affinity else {"cpus": len(affinity[1]), "of": len(affinity[0])}
-        if world == 1 and not args.no_extras:
+        if not args.no_extras:  # rank 0 at every N (the other ranks wait at the closing barrier)
             try:
                 v, sample, _, _, _ = cpu_oracle_rate(n, m, main_res["method"], args.cpu_seconds, os.cpu_count() or 1)
                 out["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": os.cpu_count() or 1, "kind": "port",
@@ -462,6 +556,7 @@ def main():
             except Exception as exc:  # noqa: BLE001  (the oracle is test infrastructure: never lose the GPU line to it)
                 out["cpu_baseline"] = {"value": None, "unit": "agent-steps/s", "cores": os.cpu_count() or 1, "kind": "port",
                                        "sample": "failed: %s" % str(exc)[:200]}
+            out["cpu_baseline"]["python_reference"] = python_reference_rate()
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()

@@ -151,7 +151,7 @@ __device__ __forceinline__ int warp_max(int v) {
 
 // Block-wide reduction of per-thread statistics into this CTA's slot (accumulating across launches;
 // one writer per slot, no atomics, so the totals are reproducible for a fixed launch geometry).
-__device__ void block_stats_commit(double *red /*smem [nwarps*6]*/, double *slot, double v0, double v1, double v2,
+__device__ void block_stats_commit(double *red /*smem [nwarps*7], at most 64 doubles: 9 warps*/, double *slot, double v0, double v1, double v2,
                                    double v3, double v4, int vmax, double v6, int nthreads) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = nthreads >> 5;
   v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3); v4 = warp_sum(v4);

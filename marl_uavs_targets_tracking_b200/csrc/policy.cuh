@@ -113,7 +113,8 @@ uavsim_policy_kernel(const float *__restrict__ obs, int64_t rows, const PolicyDe
 #pragma unroll
       for (int a = 0; a < AP; a++) { lg[a] = expf(lg[a] - mx); sum += lg[a]; }
       const Philox4 rn = philox4x32_10((uint32_t)r, (uint32_t)(r >> 32), (uint32_t)counter, (uint32_t)(counter >> 32), seed);
-      const float u = (float)philox_u53(rn.v[0], rn.v[1]) * sum;
+      // (the 53-bit uniform can round UP to 1.0f: clamped below 1, or a zero-probability last action could be drawn)
+      const float u = fminf((float)philox_u53(rn.v[0], rn.v[1]), 0x1.fffffep-1f) * sum;
       // inverse CDF: the action is the number of prefix sums that do not exceed u, capped at the last action
       float run = 0.f;
       int act = 0;

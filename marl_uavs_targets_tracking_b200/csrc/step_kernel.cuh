@@ -466,6 +466,7 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
                    int64_t env_count, int epb_rt, int mode, double coop, int done_flag,
                    double *__restrict__ stats_partial) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  static_assert((NT / 32) * 7 <= 64, "block_stats_commit: the 64-double reduction buffer holds 7 values per warp");
   const int n = CN ? CN : P.n, m = CM ? CM : P.m;
   const int epb = CN ? NT / CN : epb_rt;  // environments per CTA: the host passes NT / n, a constant when n is
   constexpr bool WARP_ENV = (CN > 0) && (CN % 32 == 0);
@@ -499,10 +500,11 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
       const int64_t grp_n = grp + gridDim.x;
       if (grp_n < ngroups) {
         const int64_t e0n = env_begin + grp_n * epb;
+        const int nen = (int)min((int64_t)epb, env_begin + env_count - e0n);  // the last group may be partial: stay inside the arrays
         auto pf = [](const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); };
-        for (int q = tid * 16; q < epb * n; q += NT * 16) { pf(B.ux + e0n * n + q); pf(B.uy + e0n * n + q); pf(B.uh + e0n * n + q); }
-        for (int q = tid * 32; q < epb * n; q += NT * 32) { pf(B.ua + e0n * n + q); pf(B.actions + e0n * n + q); }
-        for (int q = tid * 16; q < epb * m; q += NT * 16) { pf(B.tx + e0n * m + q); pf(B.ty + e0n * m + q); pf(B.th + e0n * m + q); }
+        for (int q = tid * 16; q < nen * n; q += NT * 16) { pf(B.ux + e0n * n + q); pf(B.uy + e0n * n + q); pf(B.uh + e0n * n + q); }
+        for (int q = tid * 32; q < nen * n; q += NT * 32) { pf(B.ua + e0n * n + q); pf(B.actions + e0n * n + q); }
+        for (int q = tid * 16; q < nen * m; q += NT * 16) { pf(B.tx + e0n * m + q); pf(B.ty + e0n * m + q); pf(B.th + e0n * m + q); }
       }
     }
     __syncthreads();                // previous iteration's readers are done; dth table visible

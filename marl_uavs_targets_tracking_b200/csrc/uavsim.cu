@@ -10,6 +10,9 @@
 // SURVEY.md section 7), compiled with -fmad=false so the parity-critical expressions keep the
 // reference's evaluation order.  Range tests compare squared distances against the exact squared
 // threshold computed on the host (largest double s with sqrt(s) <= thr), and take sqrt only on hits.
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 #include "step_kernel.cuh"
 #include "pmi_kernel.cuh"
@@ -36,6 +39,8 @@ static double exact_sq_threshold(double thr, bool strict) {
 static int raise_dynamic_smem(const void *fn, int device, size_t bytes) {
   static struct { const void *fn; int device; size_t bytes; } seen[256];
   static int nseen = 0;
+  static std::mutex mu;  // handles may be created from several threads
+  std::lock_guard<std::mutex> lock(mu);
   int slot = -1;
   for (int k = 0; k < nseen; k++) if (seen[k].fn == fn && seen[k].device == device) slot = k;
   if (slot < 0 && nseen < 256) { slot = nseen++; seen[slot].fn = fn; seen[slot].device = device; seen[slot].bytes = 0; }
@@ -89,10 +94,25 @@ extern "C" const char *uavsim_last_error(void) { return g_err; }
 extern "C" int64_t uavsim_launch_count(const uavsim_t *h) { return h ? h->launches : 0; }
 extern "C" int64_t uavsim_step_count(const uavsim_t *h) { return h ? h->t : 0; }
 
+static int uavsim_create_impl(const UavSimParams *p, int64_t n_envs, int64_t env_id_offset, int device, uavsim_t **out);
+
+// Every failure after the handle exists goes through uavsim_destroy (device tables, statistics, streams, events).
 extern "C" int uavsim_create(const UavSimParams *p, int64_t n_envs, int64_t env_id_offset, int device,
                              uavsim_t **out) {
   if (!p || !out) { SET_ERR("uavsim_create: NULL argument"); return UAVSIM_ERR_ARG; }
   *out = nullptr;
+  const int rc = uavsim_create_impl(p, n_envs, env_id_offset, device, out);
+  if (rc && *out) {
+    char msg[sizeof(g_err)];
+    memcpy(msg, g_err, sizeof(msg));  // keep the first error: destroy may overwrite it
+    uavsim_destroy(*out);
+    memcpy(g_err, msg, sizeof(msg));
+    *out = nullptr;
+  }
+  return rc;
+}
+
+static int uavsim_create_impl(const UavSimParams *p, int64_t n_envs, int64_t env_id_offset, int device, uavsim_t **out) {
   if (n_envs <= 0 || p->n_uav <= 0 || p->m_targets <= 0 || p->na < 2 || p->dp <= 0 || p->dc <= 0) {
     SET_ERR("uavsim_create: need n_envs>0, n_uav>0, m_targets>0, na>=2, dp>0, dc>0");
     return UAVSIM_ERR_ARG;
@@ -111,6 +131,7 @@ extern "C" int uavsim_create(const UavSimParams *p, int64_t n_envs, int64_t env_
   CUDA_TRY(cudaSetDevice(device));
   uavsim *h = (uavsim *)calloc(1, sizeof(uavsim));
   if (!h) { SET_ERR("out of host memory"); return UAVSIM_ERR_ARG; }
+  *out = h;  // from here on a failure is cleaned up by the caller through uavsim_destroy
   h->hp = *p;
   h->device = device;
   h->E = n_envs;
@@ -173,7 +194,8 @@ extern "C" int uavsim_create(const UavSimParams *p, int64_t n_envs, int64_t env_
 
   // per action: dt * discrete_action(a) (src/agent/uav.py:73-81, :96) in the reference's evaluation order,
   // plus its cosine / sine for the angle-addition update of the observation heading terms
-  double *dth = (double *)malloc(sizeof(double) * 3 * p->na);
+  std::vector<double> dth_v(3 * (size_t)p->na);
+  double *dth = dth_v.data();
   for (int a = 0; a < p->na; a++) {
     const int na1 = a + 1;
     const double rate = (double)(2 * na1 - p->na - 1) * p->uav_h_max / (double)(p->na - 1);
@@ -184,13 +206,11 @@ extern "C" int uavsim_create(const UavSimParams *p, int64_t n_envs, int64_t env_
   CUDA_TRY(cudaMalloc(&h->d_dth, sizeof(double) * 3 * p->na));
   CUDA_TRY(cudaMemcpy(h->d_dth, dth, sizeof(double) * 3 * p->na, cudaMemcpyHostToDevice));
   {  // the same table for the fast kernel: the angle in fp64, its cosine / sine in fp32
-    ActEntry *tab = (ActEntry *)malloc(sizeof(ActEntry) * p->na);
+    std::vector<ActEntry> tab(p->na);
     for (int a = 0; a < p->na; a++) { tab[a].dth = dth[3 * a]; tab[a].cd = (float)dth[3 * a + 1]; tab[a].sd = (float)dth[3 * a + 2]; }
     CUDA_TRY(cudaMalloc(&h->d_act, sizeof(ActEntry) * p->na));
-    CUDA_TRY(cudaMemcpy(h->d_act, tab, sizeof(ActEntry) * p->na, cudaMemcpyHostToDevice));
-    free(tab);
+    CUDA_TRY(cudaMemcpy(h->d_act, tab.data(), sizeof(ActEntry) * p->na, cudaMemcpyHostToDevice));
   }
-  free(dth);
 
   // launch geometry of the step kernel: one thread per UAV, nt / n environments per CTA.  Small CTAs keep the
   // phase barriers cheap (the exact pass has data-dependent length); compile-time sizes for the two headline scenarios
@@ -209,7 +229,6 @@ extern "C" int uavsim_create(const UavSimParams *p, int64_t n_envs, int64_t env_
   h->smem_step = step_smem_bytes(k.n, k.m, k.na, epb);
   if (h->smem_step > 227 * 1024) {
     SET_ERR("uavsim_create: n_uav=%d m_targets=%d needs %zu B shared memory per CTA", k.n, k.m, h->smem_step);
-    free(h);
     return UAVSIM_ERR_UNSUPPORTED;
   }
   for (int v = 0; v < 2; v++) {

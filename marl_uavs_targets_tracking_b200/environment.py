@@ -46,24 +46,26 @@ class _UavView:
         self._env, self._i = env, i
 
     def get_local_state(self):
-        return self._env._obs[0, self._i].double().cpu().numpy()
+        return self._env._host0()["obs"][self._i].copy()
 
-    x = property(lambda s: float(s._env._ux[0, s._i]))
-    y = property(lambda s: float(s._env._uy[0, s._i]))
-    h = property(lambda s: float(s._env._uh[0, s._i]))
-    a = property(lambda s: int(s._env._ua[0, s._i]))
+    # every attribute reads the per-step host snapshot of environment 0 (one device->host copy per step, not one
+    # synchronisation per attribute)
+    x = property(lambda s: float(s._env._host0()["ux"][s._i]))
+    y = property(lambda s: float(s._env._host0()["uy"][s._i]))
+    h = property(lambda s: float(s._env._host0()["uh"][s._i]))
+    a = property(lambda s: int(s._env._host0()["ua"][s._i]))
     dp = property(lambda s: s._env._params.dp)
     dc = property(lambda s: s._env._params.dc)
-    reward = property(lambda s: float(s._env._rew4[0, 0, s._i]))
+    reward = property(lambda s: float(s._env._host0()["rew"][0, s._i]))
 
 
 class _TargetView:
     def __init__(self, env, j):
         self._env, self._j = env, j
 
-    x = property(lambda s: float(s._env._tx[0, s._j]))
-    y = property(lambda s: float(s._env._ty[0, s._j]))
-    h = property(lambda s: float(s._env._th[0, s._j]))
+    x = property(lambda s: float(s._env._host0()["tx"][s._j]))
+    y = property(lambda s: float(s._env._host0()["ty"][s._j]))
+    h = property(lambda s: float(s._env._host0()["th"][s._j]))
 
 
 class BatchedEnvironment:
@@ -88,6 +90,7 @@ class BatchedEnvironment:
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self._h = None
+        self._host = None
         self._params = None
         self._episode = 0
         self._pmi_key = None
@@ -186,15 +189,37 @@ class BatchedEnvironment:
         return {"ux": self._ux, "uy": self._uy, "uh": self._uh, "ua": self._ua, "tx": self._tx, "ty": self._ty,
                 "th": self._th}
 
+    def _host0(self):
+        """Host snapshot of environment 0 (observations, rewards, state, covered count), fetched with ONE packed
+        device->host copy and kept until the next step / reset / set_state.  The reference-shaped API (n_envs == 1,
+        `uav_list[i].get_local_state()`, traces) reads it instead of synchronising once per value."""
+        if self._host is None:
+            n, m = self.n_uav, self.m_targets
+            parts = [self._obs[0].reshape(-1).double(), self._rew4[:, 0, :].reshape(-1).double(), self._ux[0], self._uy[0],
+                     self._uh[0], self._ua[0].double(), self._tx[0], self._ty[0], self._th[0], self._covered[:1].double()]
+            flat = torch.cat(parts).cpu().numpy()
+            o = 0
+
+            def take(k):
+                nonlocal o
+                v = flat[o:o + k]
+                o += k
+                return v
+            self._host = {"obs": take(n * 12).reshape(n, 12), "rew": take(4 * n).reshape(4, n), "ux": take(n), "uy": take(n),
+                          "uh": take(n), "ua": take(n).astype(np.int64), "tx": take(m), "ty": take(m), "th": take(m),
+                          "covered": int(take(1)[0])}
+        return self._host
+
     def _clear_traces(self):
+        self._host = None
         self.position = {"all_uav_xs": [], "all_uav_ys": [], "all_target_xs": [], "all_target_ys": []}
         self.covered_target_num = []
 
     def get_states(self):
         """Environment.get_states (src/environment.py:109-118)."""
         if self.n_envs == 1:
-            o = self._obs[0].double().cpu().numpy()
-            return [o[i] for i in range(self.n_uav)]
+            o = self._host0()["obs"]
+            return [o[i].copy() for i in range(self.n_uav)]
         return self._obs
 
     def _mode(self, config, pmi):
@@ -251,6 +276,7 @@ class BatchedEnvironment:
             self._actions.copy_(actions.reshape(self._actions.shape), non_blocking=True)
         with torch.cuda.device(self.device):
             _cabi.check(self._lib.uavsim_step(self._h, mode, coop, self._stream()), "uavsim_step")
+        self._host = None
         return self._obs, self._rew4, self._covered
 
     def run_random_policy(self, config, pmi, seed, first_step, nsteps):
@@ -264,6 +290,7 @@ class BatchedEnvironment:
         with torch.cuda.device(self.device):
             _cabi.check(self._lib.uavsim_run_random_policy(self._h, mode, coop, C.c_uint64(seed), int(first_step),
                                                            int(nsteps), self._stream()), "uavsim_run_random_policy")
+        self._host = None
         return self._obs, self._rew4, self._covered
 
     def step_host(self, config, pmi, h_actions, h_obs=None, h_rew4=None, h_covered=None, chunks=4):
@@ -276,6 +303,7 @@ class BatchedEnvironment:
         with torch.cuda.device(self.device):
             _cabi.check(self._lib.uavsim_step_host(self._h, mode, coop, ptr(h_actions), ptr(h_obs), ptr(h_rew4),
                                                    ptr(h_covered), int(chunks), self._stream()), "uavsim_step_host")
+        self._host = None
 
     @property
     def actions(self):
@@ -290,6 +318,7 @@ class BatchedEnvironment:
         assert obs.dtype == torch.float32 and obs.is_contiguous() and obs.numel() == self.n_envs * self.n_uav * 12
         assert obs.device == self._obs.device
         self._obs = obs.view(self.n_envs, self.n_uav, 12)
+        self._host = None
         self._bind()
 
     def bind_actions(self, actions):
@@ -314,18 +343,20 @@ class BatchedEnvironment:
             a = torch.as_tensor(np.asarray(actions, dtype=np.int32), device=self.device)
         obs, rew4, covered = self.step_device(config, pmi, a)
         if self.trace:
-            self.position["all_uav_xs"].append(self._ux[0].tolist())
-            self.position["all_uav_ys"].append(self._uy[0].tolist())
-            self.position["all_target_xs"].append(self._tx[0].tolist())
-            self.position["all_target_ys"].append(self._ty[0].tolist())
+            h0 = self._host0()
+            self.position["all_uav_xs"].append(h0["ux"].tolist())
+            self.position["all_uav_ys"].append(h0["uy"].tolist())
+            self.position["all_target_xs"].append(h0["tx"].tolist())
+            self.position["all_target_ys"].append(h0["ty"].tolist())
         if self.n_envs == 1:
-            r = rew4[:, 0, :].double().cpu().numpy()
+            h0 = self._host0()
+            r = h0["rew"]
             reward = {k: [r[q, i] for i in range(self.n_uav)] for q, k in enumerate(_REWARD_KEYS)}
-            cov = int(covered[0])
+            cov = h0["covered"]
             self.covered_target_num.append(cov)
             return self.get_states(), reward, cov
         if self.trace:
-            self.covered_target_num.append(int(covered[0]))
+            self.covered_target_num.append(self._host0()["covered"])
         return obs, {k: rew4[q] for q, k in enumerate(_REWARD_KEYS)}, covered
 
     # ------------------------------------------------------------------ extra outputs

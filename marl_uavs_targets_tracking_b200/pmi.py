@@ -79,13 +79,40 @@ class PMINetwork(nn.Module):
         bs = config["pmi"]["batch_size"]
         nb = self.b2_size // bs
         total = torch.zeros((), device=dev, dtype=torch.float64)  # the reference sums python floats
+        # Several ranks training one policy must also share ONE reward network (each rank folds its PMI into its own
+        # environment): gradients are averaged over the ranks before every optimizer step, and the BatchNorm running
+        # statistics -- updated from each rank's own batches -- are averaged after the pass, so parameters, buffers
+        # and Adam state stay identical on all ranks (tests/test_host_logic.py, world size 2 over gloo).
+        import torch.distributed as dist
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        params = [p for p in self.parameters() if p.requires_grad]
         for i in range(nb):
             self.optimizer.zero_grad()
             batch = selected[i * bs:(i + 1) * bs]
             loss = self.pair_loss(self.forward(batch[:, 0]), self.forward(batch[:, 1]))
             total = total + loss.detach().abs().double()
             loss.backward()
+            if world > 1:
+                flat = torch.cat([p.grad.reshape(-1) for p in params])
+                dist.all_reduce(flat)
+                flat /= world
+                o = 0
+                for p in params:
+                    p.grad.copy_(flat[o:o + p.numel()].view_as(p.grad))
+                    o += p.numel()
             self.optimizer.step()
+        if world > 1:
+            with torch.no_grad():
+                bufs = [b for name, b in self.named_buffers() if b.dtype.is_floating_point]
+                flat = torch.cat([b.reshape(-1) for b in bufs])
+                dist.all_reduce(flat)
+                flat /= world
+                o = 0
+                for b in bufs:
+                    b.copy_(flat[o:o + b.numel()].view_as(b))
+                    o += b.numel()
+                dist.all_reduce(total)
+                total /= world
         return float(total / nb)  # one device->host sync per call instead of one per minibatch
 
     def save(self, save_dir, epoch_i):

@@ -35,7 +35,10 @@ class PrioritizedReplayBuffer:
         self._h = C.c_void_p()
         _cabi.check(self._lib.uavsim_replay_create(self.capacity, self.state_dim, self.alpha, self.device.index or 0,
                                                    C.byref(self._h)), "uavsim_replay_create")
-        self.seed, self._draws = int(seed), 0
+        # every rank keeps its own ring: its draws must not repeat rank 0's
+        import torch.distributed as dist
+        rank = dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
+        self.seed, self._draws = (int(seed) + 0xD1B54A32D192ED03 * rank) & 0xFFFFFFFFFFFFFFFF, 0
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None

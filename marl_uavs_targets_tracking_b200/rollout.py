@@ -89,7 +89,33 @@ class BatchedActorCritic:
         # rollout policy step: the fused kernel draws from Philox (seed; row, call number); fused=False is the stock
         # torch forward + multinomial
         self.fused = bool(fused) and torch.device(device).type == "cuda" and state_dim == 12 and action_dim <= 16
-        self.seed, self._calls = int(seed), 0
+        # Every rank rolls out its own environments: the draws of rank r must differ from rank 0's (the Philox counter
+        # is the LOCAL row), so the rank is folded into the seed.
+        import torch.distributed as dist
+        rank = dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
+        self.seed, self._calls = (int(seed) + 0x9E3779B97F4A7C15 * rank) & 0xFFFFFFFFFFFFFFFF, 0
+
+    # ---- checkpoints in the reference's layout (src/models/actor_critic.py:181-200): actor/actor_weights_N.pth and
+    #      critic/critic_weights_N.pth, each {'model_state_dict', 'optimizer_state_dict'} with the key names of
+    #      FnnPolicyNet / FnnValueNet (a DistributedDataParallel wrapper is looked through, so no 'module.' prefix) ----
+    @staticmethod
+    def _plain(net):
+        return net.module if hasattr(net, "module") else net
+
+    def save(self, save_dir, epoch_i):
+        import os
+        for sub, net, opt in (("actor", self.actor, self.actor_optimizer), ("critic", self.critic, self.critic_optimizer)):
+            os.makedirs(os.path.join(save_dir, sub), exist_ok=True)
+            torch.save({"model_state_dict": self._plain(net).state_dict(), "optimizer_state_dict": opt.state_dict()},
+                       os.path.join(save_dir, sub, "%s_weights_%s.pth" % (sub, epoch_i)))
+
+    def load(self, actor_path, critic_path):
+        import os
+        for path, net, opt in ((actor_path, self.actor, self.actor_optimizer), (critic_path, self.critic, self.critic_optimizer)):
+            if path and os.path.exists(path):
+                checkpoint = torch.load(path, map_location=self.device)
+                self._plain(net).load_state_dict(checkpoint["model_state_dict"])
+                opt.load_state_dict(checkpoint["optimizer_state_dict"])
 
     @torch.no_grad()
     def take_actions(self, states, out=None):
