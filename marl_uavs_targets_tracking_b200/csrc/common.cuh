@@ -54,6 +54,7 @@ struct KParams {
   // environment).  s_f <= t2_dn - g: certainly inside; s_f > t2_up + g: certainly outside; between: decided in fp64.
   GuardK g_dp, g_2dp, g_dc, g_pf;
   float r_fast;   // the fast kernel serves environments whose entities stay within this distance of the map centre
+  float r_tile;   // the same for the tile kernel (its fp16 hi + lo operands carry ~22 bits of a coordinate)
   // fp32 copies of the constants the fast kernel's fp32 output arithmetic uses (no per-iteration conversions)
   float dp_f, inv_dp_f, inv_dc_f, inv_na_f, tt_hi_f, inv_tt_hi_f, dup_lo_f, inv_dup_span_f, alpha_f, beta_f, gamma_f;
   float k_ex1_f, tv_over_uv_f, cx_f, cy_f;
@@ -91,10 +92,14 @@ struct uavsim {
   size_t smem_step;
   // fast step kernel (64 x 64): [0] plain, [1] with masks / per-target counts
   bool has_fast;
-  int step_path;            // 0 auto, 1 generic kernel, 2 fast kernel (error if unusable)
+  int step_path;            // 0 auto, 1 generic kernel, 2 per-UAV fast kernel, 3 tile kernel (2, 3: error if unusable)
   FastKernelFn fast_fn[2];
   size_t smem_fast[2];
   int fast_grid_max[2];
+  // tile step kernel (64 x 64, step_tile_kernel.cuh): [0] plain, [1] with masks / per-target counts
+  FastKernelFn tile_fn[2];
+  size_t smem_tile[2];
+  int tile_grid_max[2];
   ActEntry *d_act;          // [na] per action: dt * rate (fp64), cos / sin of it (fp32)
   double *d_sctab;          // sine / cosine table of the fast kernel's heading routine
   // pmi

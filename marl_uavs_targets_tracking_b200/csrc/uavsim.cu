@@ -18,6 +18,7 @@
 #include "pmi_kernel.cuh"
 #include "pmi_tc_kernel.cuh"
 #include "step_fast_kernel.cuh"
+#include "step_tile_kernel.cuh"
 #include "aux_kernels.cuh"
 #include "replay.cuh"
 
@@ -178,6 +179,7 @@ static int uavsim_create_impl(const UavSimParams *p, int64_t n_envs, int64_t env
     double rf = 2e-6 * 16777216.0 * rmin;
     if (rf > k.rmax) rf = k.rmax;
     k.r_fast = (float)rf;
+    k.r_tile = (float)(rf < 4096.0 ? rf : 4096.0);
   }
   k.dp_f = (float)p->dp; k.inv_dp_f = (float)k.inv_dp; k.inv_dc_f = (float)k.inv_dc; k.inv_na_f = (float)k.inv_na;
   k.tt_hi_f = (float)k.tt_hi; k.inv_tt_hi_f = (float)k.inv_tt_hi; k.dup_lo_f = (float)k.dup_lo; k.inv_dup_span_f = (float)k.inv_dup_span;
@@ -253,6 +255,19 @@ static int uavsim_create_impl(const UavSimParams *p, int64_t n_envs, int64_t env
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, h->fast_fn[v], FAST_NT, h->smem_fast[v]));
       h->fast_grid_max[v] = h->sm_count * (o < 1 ? 1 : o);
       if (h->fast_grid_max[v] > h->grid_max) h->grid_max = h->fast_grid_max[v];  // statistics slots cover both kernels
+    }
+    // tile kernel (step_tile_kernel.cuh): the same swarms, one environment per 128-thread CTA
+    h->tile_fn[0] = uavsim_step_tile_kernel<false>;
+    h->tile_fn[1] = uavsim_step_tile_kernel<true>;
+    h->smem_tile[0] = sizeof(TileSmem<false>);
+    h->smem_tile[1] = sizeof(TileSmem<true>);
+    for (int v = 0; v < 2; v++) {
+      int rc = raise_dynamic_smem((const void *)h->tile_fn[v], device, h->smem_tile[v]);
+      if (rc) return rc;
+      int o = 1;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, h->tile_fn[v], TILE_NT, h->smem_tile[v]));
+      h->tile_grid_max[v] = h->sm_count * (o < 1 ? 1 : o);
+      if (h->tile_grid_max[v] > h->grid_max) h->grid_max = h->tile_grid_max[v];
     }
   }
   h->stat_slots = h->grid_max > 4096 ? h->grid_max : 4096;
@@ -471,8 +486,8 @@ extern "C" int uavsim_set_pmi_path(uavsim_t *h, int path) {
 }
 
 extern "C" int uavsim_set_step_path(uavsim_t *h, int path) {
-  if (!h || path < 0 || path > 2) { SET_ERR("uavsim_set_step_path: bad argument"); return UAVSIM_ERR_ARG; }
-  if (path == 2 && !h->has_fast) { SET_ERR("uavsim_set_step_path: the fast step kernel serves 64 x 64 swarms only"); return UAVSIM_ERR_UNSUPPORTED; }
+  if (!h || path < 0 || path > 3) { SET_ERR("uavsim_set_step_path: bad argument"); return UAVSIM_ERR_ARG; }
+  if (path >= 2 && !h->has_fast) { SET_ERR("uavsim_set_step_path: the fast step kernels serve 64 x 64 swarms only"); return UAVSIM_ERR_UNSUPPORTED; }
   h->step_path = path;
   return 0;
 }
@@ -556,10 +571,15 @@ static bool fast_path_usable(const uavsim_t *h) {
 static int launch_step_range(uavsim_t *h, int mode, double coop, int64_t e0, int64_t cnt, int done_flag, cudaStream_t st) {
   if (fast_path_usable(h)) {
     const int v = (h->buf.obs_mask || h->buf.tracker_cnt) ? 1 : 0;
-    const int grid = (int)(cnt < h->fast_grid_max[v] ? cnt : h->fast_grid_max[v]);
-    h->fast_fn[v]<<<grid, FAST_NT, h->smem_fast[v], st>>>(h->kp, h->buf, h->d_act, e0, cnt, mode, coop, done_flag, h->d_stats);
+    if (h->step_path == 2) {  // per-UAV candidate walks (kept for comparison)
+      const int grid = (int)(cnt < h->fast_grid_max[v] ? cnt : h->fast_grid_max[v]);
+      h->fast_fn[v]<<<grid, FAST_NT, h->smem_fast[v], st>>>(h->kp, h->buf, h->d_act, e0, cnt, mode, coop, done_flag, h->d_stats);
+    } else {                  // all-pairs tiles
+      const int grid = (int)(cnt < h->tile_grid_max[v] ? cnt : h->tile_grid_max[v]);
+      h->tile_fn[v]<<<grid, TILE_NT, h->smem_tile[v], st>>>(h->kp, h->buf, h->d_act, e0, cnt, mode, coop, done_flag, h->d_stats);
+    }
   } else {
-    if (h->step_path == 2) { SET_ERR("uavsim_step: the fast step kernel needs 64 x 64 swarms and 16-byte aligned buffers"); return UAVSIM_ERR_UNSUPPORTED; }
+    if (h->step_path >= 2) { SET_ERR("uavsim_step: the fast step kernel needs 64 x 64 swarms and 16-byte aligned buffers"); return UAVSIM_ERR_UNSUPPORTED; }
     const int64_t ngroups = (cnt + h->epb - 1) / h->epb;
     const int grid = (int)(ngroups < h->grid_max ? ngroups : h->grid_max);
     h->step_fn[h->buf.obs_mask ? 1 : 0]<<<grid, h->nt, h->smem_step, st>>>(h->kp, h->buf, h->d_dth, e0, cnt, h->epb, mode, coop, done_flag, h->d_stats);

@@ -253,7 +253,8 @@ class BatchedEnvironment:
             _cabi.check(self._lib.uavsim_set_pmi_path(self._h, self._pmi_path), "uavsim_set_pmi_path")
 
     def set_step_path(self, path):
-        """0 = automatic, 1 = generic step kernel, 2 = fast 64 x 64 step kernel (uavsim_set_step_path)."""
+        """0 = automatic, 1 = generic step kernel, 2 = per-UAV fast 64 x 64 kernel, 3 = all-pairs tile 64 x 64 kernel
+        (uavsim_set_step_path)."""
         self._step_path = int(path)
         if self._h is not None:
             _cabi.check(self._lib.uavsim_set_step_path(self._h, self._step_path), "uavsim_set_step_path")

@@ -1,4 +1,6 @@
-"""The fast 64 x 64 step kernel (csrc/step_fast_kernel.cuh) against the CPU oracle and against the generic kernel.
+"""The two 64 x 64 step kernels -- the all-pairs tile kernel (csrc/step_tile_kernel.cuh, step path 3, the default for
+this shape) and the per-UAV fast kernel (csrc/step_fast_kernel.cuh, step path 2) -- against the CPU oracle and against
+the generic kernel.
 
 The fast kernel classifies every pair in fp32 with a two-sided guard and sends a UAV to the fp64 path only when a
 pair falls inside the guard band; these tests pin (i) both template instances (plain, and with masks / per-target
@@ -23,15 +25,19 @@ def _env(n, m, cfg, E, **kw):
     return BatchedEnvironment(n, m, e["x_max"], e["y_max"], e["na"], n_envs=E, device="cuda:0", **kw)
 
 
+PATHS = [3, 2]
+
+
+@pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("method,T", [("MAAC-G", 200), ("MAAC", 40)])
-def test_plain_instance_matches_the_oracle(oracle, method, T):
+def test_plain_instance_matches_the_oracle(oracle, method, T, path):
     """No masks, no per-target counts: the instance the benchmark runs.  Whole episode, Philox reset and policy."""
     from marl_uavs_targets_tracking_b200 import default_config
     n = m = 64
     cfg = default_config(method, n, m)
     E = 80
     env = _env(n, m, cfg, E, seed=77)
-    env.set_step_path(2)
+    env.set_step_path(path)
     env.reset(cfg)
     P = oracle_params_from_config(cfg, n, m)
     st = {k: np.ascontiguousarray(v.cpu().numpy()) for k, v in env.get_state().items()}
@@ -55,7 +61,8 @@ def test_plain_instance_matches_the_oracle(oracle, method, T):
     env.close()
 
 
-def test_fast_and_generic_kernels_agree():
+@pytest.mark.parametrize("fast_path", PATHS)
+def test_fast_and_generic_kernels_agree(fast_path):
     """Same seeds through both kernels: every integer output identical (masks, counts, coverage, last actions), state
     equal to 1e-9 (the kernels use different sine routines, each within 2 ulp), floats within the tight tolerance."""
     from marl_uavs_targets_tracking_b200 import default_config
@@ -63,7 +70,7 @@ def test_fast_and_generic_kernels_agree():
     cfg = default_config("MAAC-G", n, m)
     E = 150
     envs = []
-    for path in (1, 2):
+    for path in (1, fast_path):
         env = _env(n, m, cfg, E, seed=5, record_masks=True, track_counts=True)
         env.set_step_path(path)
         env.reset(cfg)
@@ -91,7 +98,8 @@ def test_fast_and_generic_kernels_agree():
     f.close()
 
 
-def test_pairs_exactly_on_the_thresholds(oracle):
+@pytest.mark.parametrize("path", PATHS)
+def test_pairs_exactly_on_the_thresholds(oracle, path):
     """Entities placed so that AFTER the move d == dp (observe / track: inside; coverage: outside), d == dc for a
     partner that moved first and for one observed at its old position, d == 2 dp and d == dp between UAVs -- and the
     same geometry one ulp inside / outside.  Headings 0 / pi/2 keep the moves exact (cos 0 = 1, sin 0 = 0), so the
@@ -101,7 +109,7 @@ def test_pairs_exactly_on_the_thresholds(oracle):
     cfg = default_config("MAAC-G", n, m)
     E = 7
     env = _env(n, m, cfg, E, seed=1, record_masks=True, track_counts=True)
-    env.set_step_path(2)
+    env.set_step_path(path)
     env.reset(cfg)
     st = {k: v.cpu().numpy().copy() for k, v in env.get_state().items()}
     # park everything far apart first (a sparse lattice outside each other's ranges where possible)
@@ -147,7 +155,8 @@ def test_pairs_exactly_on_the_thresholds(oracle):
     env.close()
 
 
-def test_wide_swarms_fall_back_to_fp64_per_environment(oracle):
+@pytest.mark.parametrize("path", PATHS)
+def test_wide_swarms_fall_back_to_fp64_per_environment(oracle, path):
     """Beyond r_fast (about 33 x min(dp, dc) from the map centre) the fp32 offsets would cost more than 2e-6 in the
     observation: such an environment takes the fp64 path as a whole, its neighbours in the batch stay fast."""
     from marl_uavs_targets_tracking_b200 import default_config
@@ -155,7 +164,7 @@ def test_wide_swarms_fall_back_to_fp64_per_environment(oracle):
     cfg = default_config("MAAC-G", n, m)
     E = 6
     env = _env(n, m, cfg, E, seed=4, track_counts=True)
-    env.set_step_path(2)
+    env.set_step_path(path)
     env.reset(cfg)
     st = env.get_state()
     st["ux"][1, :] += 2.0e4
@@ -181,6 +190,7 @@ def test_fast_path_is_refused_for_other_shapes():
     cfg = default_config("MAAC", 10, 10)
     env = _env(10, 10, cfg, 4)
     env.reset(cfg)
-    with pytest.raises(UavSimError):
-        env.set_step_path(2)
+    for path in PATHS:
+        with pytest.raises(UavSimError):
+            env.set_step_path(path)
     env.close()
