@@ -31,6 +31,12 @@ struct GuardK {
   float t2_up, t2_dn, c1, c0;
 };
 
+// Decision bands of the tile step kernel for environments whose entities stay within r of the map centre: per radius
+// the centre C of the guard band and its half width H (a pair with |s_f - C| <= H is decided in fp64).
+struct TileBand {
+  float r, Cp, Hp, Cd, Hd, Cc, Hc, pad;
+};
+
 struct KParams {
   int n, m, na, num_steps;
   int64_t E;                  // environments of this handle (plane stride of rew4 is E*n)
@@ -55,6 +61,7 @@ struct KParams {
   GuardK g_dp, g_2dp, g_dc, g_pf;
   float r_fast;   // the fast kernel serves environments whose entities stay within this distance of the map centre
   float r_tile;   // the same for the tile kernel (its fp16 hi + lo operands carry ~22 bits of a coordinate)
+  TileBand tb[2]; // bands for a swarm inside / around the map, and for anything up to r_tile
   // fp32 copies of the constants the fast kernel's fp32 output arithmetic uses (no per-iteration conversions)
   float dp_f, inv_dp_f, inv_dc_f, inv_na_f, tt_hi_f, inv_tt_hi_f, dup_lo_f, inv_dup_span_f, alpha_f, beta_f, gamma_f;
   float k_ex1_f, tv_over_uv_f, cx_f, cy_f;

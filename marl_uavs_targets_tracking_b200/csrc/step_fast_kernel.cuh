@@ -9,10 +9,13 @@
 //   * Pair arithmetic in fp32 with a TWO-SIDED guard.  Positions are staged as fp32 relative to the map centre.
 //     With g(R) a proven bound on the fp32 error of a squared distance (R = largest |coordinate - centre| of the
 //     environment, KParams::GuardK): s_f <= thr^2 - g is certainly inside the radius, s_f > thr^2 + g certainly
-//     outside, and only a pair in the band between the two (about one pair in 10^6) is AMBIGUOUS.  A UAV that meets
-//     an ambiguous pair re-evaluates its whole row in fp64 with the reference's arithmetic (fast_agent_exact), so
-//     every mask, count and coverage bit is decided exactly as before -- but the candidates of an ordinary UAV never
-//     touch the fp64 pipe.  The observation sums are fp32 (outputs are fp32, contract 1e-5; measured ~2e-7).
+//     outside, and only a pair in the band between the two (about one pair in 10^5) is AMBIGUOUS.  Every walk
+//     tracks the largest squared distance it accepted; a UAV whose list held an ambiguous pair walks THAT LIST once
+//     more through a checked twin (sf_*_checked) that decides the pairs inside the band in fp64 with the reference's
+//     arithmetic, so every mask, count and coverage bit is decided exactly as before -- but the candidates of an
+//     ordinary UAV never touch the fp64 pipe.  (Until round 2 such a UAV re-evaluated its whole row -- all three
+//     lists, fp64 sums and all -- which took 13 % of the issued instructions.)
+//     The observation sums are fp32 (outputs are fp32, contract 1e-5; measured ~2e-7).
 //   * Candidate walks.  A sign-bit prefilter (packed f32x2 FMAs, as in the generic kernel) marks the partners inside
 //     each guarded radius; three short walks consume them: targets (observation + tracking reward + coverage),
 //     communication partners (new record if the partner moved first, old record otherwise: src/agent/uav.py:124-147
@@ -207,7 +210,7 @@ struct FastAgent {
 
 // ------------------------------------------------------------------------------------------------
 // exact path: the reference's arithmetic pair by pair in fp64, including the min(dist, 1) row weights of
-// src/agent/uav.py:162-186.  Taken by a UAV that met an ambiguous pair, by UAVs within 2 m of the origin in both
+// src/agent/uav.py:162-186.  Taken by UAVs within 2 m of the origin in both
 // coordinates (the only place where a row weight differs from 1) and by every UAV of an environment with an
 // entity outside the radius the fast path serves.  Cold: never inlined; its constants and mask pointers travel by
 // value (a reference to the kernel's parameter block would force a copy of the whole block into local memory at
@@ -291,6 +294,114 @@ __device__ __noinline__ void fast_agent_exact(const ExactK P, const MaskPtrs B, 
   O.tt = (float)tt; O.dup = (float)dup;
   O.nb[0] = nb[0]; O.nb[1] = nb[1];
   O.cov[0] = cov[0]; O.cov[1] = cov[1];
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Checked twins of the three candidate walks.  A walk that accepted a squared distance inside the guard band hands
+// its list to the twin, which repeats the walk and decides every pair inside the band as the reference does:
+// d2 = dx*dx + dy*dy in fp64 (no contraction) against the exact squared threshold.  Cold (about one list in a
+// hundred); never inlined, results through a struct that only the cold branch of the caller touches.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int sf_exact_pair(double bx, double by, double ax, double ay, double s_le, double s_lt) {
+  const double dx = bx - ax, dy = by - ay;
+  const double d2 = dx * dx + dy * dy;
+  return (d2 <= s_le ? 1 : 0) | (d2 <= s_lt ? 2 : 0);  // bit 0: d <= thr, bit 1: d < thr
+}
+struct WalkOwn {     // the walking UAV
+  double xi, yi;
+  float xf, yf;
+  int t;
+};
+struct TgtOut { float ox, oy, ovx, ovy, ttacc; uint32_t cvE, cvO, ncE, ncO; };
+template <int N, int M, bool AUX>
+__device__ __noinline__ void sf_targets_checked(const FastSmem<N, M, AUX> *Sp, const WalkOwn W, float T_lo, double s_le,
+                                                double s_lt, float inv_dp_f, uint32_t cvE, uint32_t cvO, TgtOut *O) {
+  const FastSmem<N, M, AUX> &S = *Sp;
+  float ox = 0, oy = 0, ovx = 0, ovy = 0, ttacc = 0;
+  uint32_t ncE = 0, ncO = 0;
+  for (int par = 0; par < 2; par++) {
+    uint32_t w = par ? cvO : cvE;
+    const float *rec = reinterpret_cast<const float *>(S.tslot) + par;
+    while (w) {
+      const int b = sf_msb(w);
+      const uint32_t bit = 1u << b;
+      w ^= bit;
+      const float *r = rec + 8 * b;
+      const float dx = r[0] - W.xf, dy = r[2] - W.yf;
+      const float s = fmaf(dx, dx, dy * dy);
+      if (s > T_lo) {
+        const int dec = sf_exact_pair(S.otx[2 * b + par], S.oty[2 * b + par], W.xi, W.yi, s_le, s_lt);
+        if (!(dec & 1)) { if (par) cvO ^= bit; else cvE ^= bit; continue; }
+        if (!(dec & 2)) { if (par) ncO |= bit; else ncE |= bit; }  // d == dp: observed and tracked, not covered
+      }
+      ox += dx; oy += dy; ovx += r[4]; ovy += r[6];
+      ttacc = fmaf(fast_sqrtf(s), -inv_dp_f, ttacc);
+    }
+  }
+  O->ox = ox; O->oy = oy; O->ovx = ovx; O->ovy = ovy; O->ttacc = ttacc;
+  O->cvE = cvE; O->cvO = cvO; O->ncE = ncE; O->ncO = ncO;
+}
+struct CommOut { float sx, sy, sc, ss, sa, cn; uint32_t cmE, cmO; };
+template <int N, int M, bool AUX>
+__device__ __noinline__ void sf_comm_checked(const FastSmem<N, M, AUX> *Sp, const WalkOwn W, float T_lo, float T_hi,
+                                             double s_le, int ihx, uint32_t w, CommOut *O) {
+  const FastSmem<N, M, AUX> &S = *Sp;
+  float sx = 0, sy = 0, sc = 0, ss = 0, sa = 0, cn = 0;
+  uint32_t cmE = 0, cmO = 0;
+  while (w) {
+    const int b = sf_msb(w);
+    const uint32_t bit = 1u << b;
+    w ^= bit;
+    const bool moved = b < ihx;  // the partner's record after its move, or before it
+    const SlotRec &rec = moved ? S.slotn[b] : S.sloto[b];
+    const double *px = moved ? S.oux : S.xo, *py = moved ? S.ouy : S.yo;
+    const float *f = reinterpret_cast<const float *>(&rec);
+    for (int h = 0; h < 2; h++) {
+      const float dx = f[h] - W.xf, dy = f[2 + h] - W.yf;
+      const float s = fmaf(dx, dx, dy * dy);
+      bool hit = s <= T_hi;
+      // (the UAV's own entry stays on the fp32 test: the caller takes it out again with the same test)
+      if (hit && s > T_lo && 2 * b + h != W.t) hit = sf_exact_pair(px[2 * b + h], py[2 * b + h], W.xi, W.yi, s_le, s_le) & 1;
+      if (hit) {
+        sx += dx; sy += dy; sc += f[4 + h]; ss += f[6 + h]; sa += f[8 + h]; cn += 1.0f;
+        if (h) cmO |= bit; else cmE |= bit;
+      }
+    }
+  }
+  O->sx = sx; O->sy = sy; O->sc = sc; O->ss = ss; O->sa = sa; O->cn = cn; O->cmE = cmE; O->cmO = cmO;
+}
+struct DupOut { float dup; uint32_t nbE, nbO, dpE, dpO; };
+template <int N, int M, bool AUX>
+__device__ __noinline__ void sf_dup_checked(const FastSmem<N, M, AUX> *Sp, const WalkOwn W, float T2_lo, float Tp_lo,
+                                            float Tp_hi, double s_2dp_le, double s_dp_le, float k_ex0, float k_ex1,
+                                            uint32_t cdE, uint32_t cdO, DupOut *O) {
+  const FastSmem<N, M, AUX> &S = *Sp;
+  float dup = 0;
+  uint32_t nb[2] = {0, 0}, dp[2] = {cdE, cdO};
+  for (int par = 0; par < 2; par++) {
+    uint32_t w = par ? cdO : cdE;
+    const unsigned char *rec = reinterpret_cast<const unsigned char *>(S.slotn) + 4 * par;
+    while (w) {
+      const int b = sf_msb(w);
+      const uint32_t bit = 1u << b;
+      w ^= bit;
+      const float *r = reinterpret_cast<const float *>(rec + 48 * b);
+      const float dx = r[0] - W.xf, dy = r[2] - W.yf;
+      const float s = fmaf(dx, dx, dy * dy);
+      if (s > T2_lo && !(sf_exact_pair(S.oux[2 * b + par], S.ouy[2 * b + par], W.xi, W.yi, s_2dp_le, s_2dp_le) & 1)) {
+        dp[par] ^= bit;
+        continue;
+      }
+      dup += fast_ex2f(fmaf(fast_sqrtf(s), k_ex1, k_ex0));
+      if (s <= Tp_hi) {
+        bool in = true;
+        if (s > Tp_lo) in = sf_exact_pair(S.oux[2 * b + par], S.ouy[2 * b + par], W.xi, W.yi, s_dp_le, s_dp_le) & 1;
+        if (in) nb[par] |= bit;
+      }
+    }
+  }
+  O->dup = dup; O->nbE = nb[0]; O->nbO = nb[1]; O->dpE = dp[0]; O->dpO = dp[1];
 }
 
 // sin / cos of a heading: the wrapped range takes the inline routine, anything else the library one (whose pointer
@@ -455,8 +566,9 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
     // neighbour set d <= dp and the targets strictly inside dp (even / odd words)
     float o0, o1, o2, o3, o4, o5, o6, o7, o8, tt_f, dup_f;
     uint32_t nbE = 0, nbO = 0, cvE = 0, cvO = 0;
+    uint32_t ncE = 0, ncO = 0;  // targets at distance exactly dp: observed and tracked, not covered
     uint32_t cmE = 0, cmO = 0, dpE = 0, dpO = 0;  // AUX: communication / duplicate sets for the mask outputs
-    bool exact = far_env || near_origin;
+    const bool exact = far_env || near_origin;
     if (!exact) {
       const float g_dp = fmaf(R, P.g_dp.c1, P.g_dp.c0), g_2dp = fmaf(R, P.g_2dp.c1, P.g_2dp.c0);
       const float g_dc = fmaf(R, P.g_dc.c1, P.g_dc.c0), g_pf = fmaf(R, P.g_pf.c1, P.g_pf.c0);
@@ -465,13 +577,12 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
       const float Tc_hi = __fadd_ru(P.g_dc.t2_up, g_dc), Tc_lo = __fadd_rd(P.g_dc.t2_dn, -g_dc);
       const float Tf_hi = __fadd_ru(P.g_pf.t2_up, g_pf);
       const uint64_t xf2 = pack2(xf, xf), yf2 = pack2(yf, yf);
-      bool amb = false;
+      const WalkOwn WO = {xi, yi, xf, yf, t};
 
       // -- targets: observe_target (uav.py:101-122), tracking reward (uav.py:199-212), coverage (environment.py:246-253)
       {
         uint32_t d0, d1;
         prefilter64<false, (int)sizeof(TSlot)>(S.tslot, xf, yf, Tp_hi, 0.f, cvE, cvO, d0, d1);
-        const int nobs = __popc(cvE) + __popc(cvO);
         float ox = 0, oy = 0, ovx = 0, ovy = 0, ttacc = 0, smax_t = 0;
 #pragma unroll
         for (int par = 0; par < 2; par++) {
@@ -489,7 +600,13 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
             ttacc = fmaf(fast_sqrtf(s), -inv_dp_f, ttacc);  // sum of (dp - d)/dp - 1
           }
         }
-        amb |= smax_t > Tp_lo;
+        if (smax_t > Tp_lo) {  // a pair inside the guard band: this list once more, checked
+          TgtOut X;
+          sf_targets_checked<N, M, AUX>(&S, WO, Tp_lo, P.s_dp_le, P.s_dp_lt, inv_dp_f, cvE, cvO, &X);
+          ox = X.ox; oy = X.oy; ovx = X.ovx; ovy = X.ovy; ttacc = X.ttacc;
+          cvE = X.cvE; cvO = X.cvO; ncE = X.ncE; ncO = X.ncO;
+        }
+        const int nobs = __popc(cvE) + __popc(cvO);
         if (nobs) {
           const float kf = (float)nobs, rk = sf_rcp(kf);
           // the own coordinate's fp32 rounding is common to every row: taken out of the mean exactly
@@ -542,8 +659,8 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
           if (AUX) { if (h0) cmE |= bit; if (h1) cmO |= bit; }
         }
         // own entry of the own slot: the record that was read there (new if this UAV sits in the odd place, else old)
-        // (the own entry also went into smax_c: its distance is 0 or one move, far from the band unless dt*v ~ dc,
-        // and then the exact path takes over -- slower, still right)
+        // (the own entry also went into smax_c: its distance is 0 or one move, far from the band unless dt*v ~ dc; the
+        // checked twin keeps it on this same fp32 test)
         float own_w, own_dx, own_dy, own_c, own_s, own_a;
         {
           const float *r = reinterpret_cast<const float *>(slot_new + (ic ? 0u : OLD_OFF) + 48 * ih) + ic;
@@ -551,16 +668,23 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
           const float s_own = fmaf(own_dx, own_dx, own_dy * own_dy);
           own_w = sf_le(s_own, Tc_hi);
         }
-        const float cntf = (f2_lo(cn) + f2_hi(cn)) - own_w;
-        amb |= smax_c > Tc_lo;
+        float tsx = f2_lo(sx) + f2_hi(sx), tsy = f2_lo(sy) + f2_hi(sy), tsc = f2_lo(sc) + f2_hi(sc);
+        float tss = f2_lo(ss) + f2_hi(ss), tsa = f2_lo(sa) + f2_hi(sa), tcn = f2_lo(cn) + f2_hi(cn);
+        if (smax_c > Tc_lo) {  // a pair inside the guard band: this list once more, checked
+          CommOut X;
+          sf_comm_checked<N, M, AUX>(&S, WO, Tc_lo, Tc_hi, P.s_dc_le, ihx, ccE | ccO, &X);
+          tsx = X.sx; tsy = X.sy; tsc = X.sc; tss = X.ss; tsa = X.sa; tcn = X.cn;
+          if (AUX) { cmE = X.cmE; cmO = X.cmO; }
+        }
+        const float cntf = tcn - own_w;
         if (AUX) { if (ic) cmO &= ~(1u << ih); else cmE &= ~(1u << ih); }
         if (cntf > 0.5f) {
           const float rk = sf_rcp(cntf);
-          o0 = fmaf((f2_lo(sx) + f2_hi(sx)) - own_w * own_dx, rk, -xl) * inv_dc_f;
-          o1 = fmaf((f2_lo(sy) + f2_hi(sy)) - own_w * own_dy, rk, -yl) * inv_dc_f;
-          o2 = fmaf((f2_lo(sc) + f2_hi(sc)) - own_w * own_c, rk, -chf);
-          o3 = fmaf((f2_lo(ss) + f2_hi(ss)) - own_w * own_s, rk, -shf);
-          o4 = (((f2_lo(sa) + f2_hi(sa)) - own_w * own_a) - cntf * (float)ai) * (rk * inv_na_f);
+          o0 = fmaf(tsx - own_w * own_dx, rk, -xl) * inv_dc_f;
+          o1 = fmaf(tsy - own_w * own_dy, rk, -yl) * inv_dc_f;
+          o2 = fmaf(tsc - own_w * own_c, rk, -chf);
+          o3 = fmaf(tss - own_w * own_s, rk, -shf);
+          o4 = ((tsa - own_w * own_a) - cntf * (float)ai) * (rk * inv_na_f);
         } else {
           o0 = o1 = o2 = o3 = o4 = -1.f;
         }
@@ -589,10 +713,14 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
           }
           if (par) nbO = nbits; else nbE = nbits;
         }
-        amb |= (smax_d > T2_lo) || (smax_n > Tp_lo);
+        if ((smax_d > T2_lo) || (smax_n > Tp_lo)) {  // a pair inside a guard band: this list once more, checked
+          DupOut X;
+          sf_dup_checked<N, M, AUX>(&S, WO, T2_lo, Tp_lo, Tp_hi, P.s_2dp_le, P.s_dp_le, k_ex0, k_ex1, cdE, cdO, &X);
+          dup = X.dup; nbE = X.nbE; nbO = X.nbO;
+          if (AUX) { dpE = X.dpE; dpO = X.dpO; }
+        }
         dup_f = -0.5f * dup;
       }
-      exact = amb;
     }
     if (exact) {
       const ExactK XK = {P.s_dp_le, P.s_dp_lt, P.s_2dp_le, P.s_dc_le, P.dp, P.dc, P.two_dp, P.na};
@@ -607,12 +735,13 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
       for (int j = 0; j < 64; j++) {
         const int b = j >> 1;
         const uint8_t v = (((j & 1) ? cvO : cvE) >> b) & 1u;
-        B.obs_mask[mrow_t + j] = v; B.cover_mask[mrow_t + j] = v;
+        B.obs_mask[mrow_t + j] = v; B.cover_mask[mrow_t + j] = v & ~((((j & 1) ? ncO : ncE) >> b) & 1u);
         B.comm_mask[mrow_u + j] = (((j & 1) ? cmO : cmE) >> b) & 1u;
         B.nbr_mask[mrow_u + j] = (((j & 1) ? nbO : nbE) >> b) & 1u;
         B.dup_mask[mrow_u + j] = (((j & 1) ? dpO : dpE) >> b) & 1u;
       }
     }
+    cvE &= ~ncE; cvO &= ~ncO;  // from here on: the targets strictly inside dp
     if (AUX && B.tracker_cnt) {
 #pragma unroll
       for (int par = 0; par < 2; par++) {

@@ -38,7 +38,7 @@
 #ifndef TILE_CTAS_PER_SM
 #define TILE_CTAS_PER_SM 5
 #endif
-#define TILE_SUM_W 20  // floats per UAV in the sums array (80 B rows: conflict-free 128-bit reads)
+#define TILE_SUM_W 28  // floats per UAV in the sums array (112 B rows: conflict-free 128-bit reads)
 
 struct __align__(16) TileFeat {
   float c, s, a, pad;  // cos h, sin h, action index
@@ -98,6 +98,11 @@ __device__ __forceinline__ float tl_min3abs(float a, float b, float c) {
   asm("min.abs.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
   return r;
 }
+__device__ __forceinline__ float tl_min3(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
 // smallest |value| of four packed pairs
 __device__ __forceinline__ float tl_band4(uint64_t u0, uint64_t u1, uint64_t u2, uint64_t u3) {
   float m = tl_min3abs(f2_lo(u0), f2_hi(u0), f2_lo(u1));
@@ -118,11 +123,21 @@ __device__ __forceinline__ void tl_ldb4(uint32_t addr, uint32_t &b0, uint32_t &b
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(addr));
 }
-// v = hi + lo in fp16 (hi in the low half)
-__device__ __forceinline__ uint32_t tl_split(float v) {
-  const __half hi = __float2half_rn(v);
-  const __half lo = __float2half_rn(v - __half2float(hi));
-  return (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
+// (a, b) = hi + lo in fp16: {a hi, b hi} and {a lo, b lo}, one packed conversion each
+__device__ __forceinline__ void tl_split2(float a, float b, uint32_t &hi2, uint32_t &lo2) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 back = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - back.x, b - back.y);
+  hi2 = *reinterpret_cast<const uint32_t *>(&h);
+  lo2 = *reinterpret_cast<const uint32_t *>(&l);
+}
+// one B row {a hi, b hi, a lo, b lo, c hi, d hi, c lo, d lo}: the sums of hi and lo parts land in neighbouring quads of the
+// accumulator and are added when the UAV is finished
+__device__ __forceinline__ uint4 tl_brow(float a, float b, float c, float d) {
+  uint4 r;
+  tl_split2(a, b, r.x, r.y);
+  tl_split2(c, d, r.z, r.w);
+  return r;
 }
 __device__ __forceinline__ uint64_t tl_set_half(uint64_t u, int half, float v) {
   const uint64_t b = (uint64_t)__float_as_uint(v);
@@ -153,6 +168,9 @@ __device__ __noinline__ void tile_fix(const double *rx, const double *ry, const 
     }
   }
 }
+
+// inverse of the fp16 value of bit 10 + J (0x0400, 0x0800, 0x1000, 0x2000 = 2^-14, 2^-13, 2^-11, 2^-7)
+__device__ __forceinline__ float tl_nscale(int J) { return J == 0 ? 16384.f : (J == 1 ? 8192.f : (J == 2 ? 2048.f : 128.f)); }
 
 // what the exact path produces for one UAV
 struct TileAgent {
@@ -331,7 +349,7 @@ uavsim_step_tile_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
       float *ts = reinterpret_cast<float *>(&S.tpos[j >> 1]) + (j & 1);
       ts[0] = txf; ts[2] = tyf;
       S.tfe[j] = make_float2(vx, vy);
-      S.bt1[j] = make_uint4(tl_split(txf), tl_split(tyf), tl_split(vx), tl_split(vy));
+      S.bt1[j] = tl_brow(txf, tyf, vx, vy);
       rabs = fmaxf(fabsf(txf), fabsf(tyf));
       if (AUX) S.tcnt[j] = 0;
     } else {
@@ -346,7 +364,7 @@ uavsim_step_tile_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
       float *so = reinterpret_cast<float *>(&S.opos[t >> 1]) + (t & 1);
       so[0] = xof; so[2] = yof;
       S.ofe[t] = TileFeat{cof, sof, (float)a_old, 0.f};
-      S.bo1[t] = make_uint4(tl_split(xof), tl_split(yof), tl_split(cof), tl_split(sof));
+      S.bo1[t] = tl_brow(xof, yof, cof, sof);
       S.bo2[t] = make_uint4(0x3C00u | ((uint32_t)__half_as_ushort(__float2half_rn((float)a_old)) << 16), 0u, 0u, 0u);
       x += P.dtv_u * ch;
       y += P.dtv_u * sh;
@@ -370,7 +388,7 @@ uavsim_step_tile_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
       float *sn = reinterpret_cast<float *>(&S.npos[t >> 1]) + (t & 1);
       sn[0] = xf; sn[2] = yf;
       S.nfe[t] = TileFeat{chf, shf, (float)act, 0.f};
-      S.bn1[t] = make_uint4(tl_split(xf), tl_split(yf), tl_split(chf), tl_split(shf));
+      S.bn1[t] = tl_brow(xf, yf, chf, shf);
       S.bn2[t] = make_uint4(0x3C00u | ((uint32_t)__half_as_ushort(__float2half_rn((float)act)) << 16), 0u, 0u, 0u);
       rabs = fmaxf(fmaxf(fabsf(xf), fabsf(yf)), fmaxf(fabsf(xof), fabsf(yof)));
       // fp16 carries action indices exactly up to 2048: anything else takes the exact path
@@ -390,23 +408,16 @@ uavsim_step_tile_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
 
     const float R = __uint_as_float(max(max(S.rmax[0], S.rmax[1]), max(S.rmax[2], S.rmax[3])));
     const bool slow0 = !(R <= P.r_tile);
-    uint32_t nbrbits = 0;  // pair (J, k, half) -> bit 4 J + k + 16 half
+    // neighbour decisions of this thread's pairs: register kk (the A-fragment slot), column tile J -> bit 10 + J of
+    // each half.  Read as fp16 these single bits are the weights 2^-14, 2^-13, 2^-11, 2^-7: the B rows of column tile J
+    // carry the inverse factor (tl_nscale), so the neighbour mean needs no rebuilt weights.
+    uint32_t nw[4] = {0u, 0u, 0u, 0u};
 
     if (!slow0) {
       // ================= phase 1: all pairs of the 16 rows of this warp =================
       // band centre and half width per radius: certainly inside below C - H, certainly outside above C + H
-      float Cp, Hp, Cd, Hd, Cc, Hc;
-      {
-        auto band = [&](const GuardK &G, float &C, float &H) {
-          const float gd = fmaf(R, G.c1, G.c0);
-          const float hi = __fadd_ru(G.t2_up, gd), lo = __fadd_rd(G.t2_dn, -gd);
-          C = 0.5f * (hi + lo);
-          H = __fadd_ru(__fmul_ru(0.5f, __fadd_ru(hi, -lo)), C * 4.8e-7f);
-        };
-        band(P.g_dp, Cp, Hp);
-        band(P.g_2dp, Cd, Hd);
-        band(P.g_dc, Cc, Hc);
-      }
+      const TileBand &TB = P.tb[(R <= P.tb[0].r) ? 0 : 1];
+      const float Cp = TB.Cp, Hp = TB.Hp, Cd = TB.Cd, Hd = TB.Hd, Cc = TB.Cc, Hc = TB.Hc;
       const uint64_t nCp2 = pack2(-Cp, -Cp), nCd2 = pack2(-Cd, -Cd), nCc2 = pack2(-Cc, -Cc), Cp2 = pack2(Cp, Cp);
       uint64_t xr0, yr0, xr1, yr1;
       {
@@ -543,10 +554,12 @@ uavsim_step_tile_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
           tile_fix(S.oux, S.ouy, S.oux, S.ouy, r0, col0, P.s_2dp_le, P.s_2dp_le, Hd, 15, uu, &S.slow);
           d0 = uu[0]; d1 = uu[1]; d2 = uu[2]; d3 = uu[3];
         }
-        const uint32_t anyd = (uint32_t)d0 | (uint32_t)(d0 >> 32) | (uint32_t)d1 | (uint32_t)(d1 >> 32) | (uint32_t)d2 |
-                              (uint32_t)(d2 >> 32) | (uint32_t)d3 | (uint32_t)(d3 >> 32);
+        float anyd = tl_min3(f2_lo(d0), f2_hi(d0), f2_lo(d1));
+        anyd = tl_min3(anyd, f2_hi(d1), f2_lo(d2));
+        anyd = tl_min3(anyd, f2_hi(d2), f2_lo(d3));
+        anyd = fminf(anyd, f2_hi(d3));
         uint32_t nsig[4] = {0, 0, 0, 0};
-        if (__any_sync(0xffffffffu, (int)anyd < 0)) {
+        if (__any_sync(0xffffffffu, anyd < 0.f)) {
           const float e00 = fast_ex2f(fmaf(fast_sqrtf(f2_lo(s0)), k_ex1, k_ex0)), e01 = fast_ex2f(fmaf(fast_sqrtf(f2_hi(s0)), k_ex1, k_ex0));
           const float e10 = fast_ex2f(fmaf(fast_sqrtf(f2_lo(s1)), k_ex1, k_ex0)), e11 = fast_ex2f(fmaf(fast_sqrtf(f2_hi(s1)), k_ex1, k_ex0));
           const float e20 = fast_ex2f(fmaf(fast_sqrtf(f2_lo(s2)), k_ex1, k_ex0)), e21 = fast_ex2f(fmaf(fast_sqrtf(f2_hi(s2)), k_ex1, k_ex0));
@@ -567,8 +580,8 @@ uavsim_step_tile_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
               p0 = uu[0]; p1 = uu[1]; p2 = uu[2]; p3 = uu[3];
             }
             nsig[0] = tl_signs(p0); nsig[1] = tl_signs(p1); nsig[2] = tl_signs(p2); nsig[3] = tl_signs(p3);
-            const uint32_t K0 = 0x00010001u << (4 * J);
-            nbrbits |= (nsig[0] & K0) | (nsig[1] & (K0 << 1)) | (nsig[2] & (K0 << 2)) | (nsig[3] & (K0 << 3));
+            const uint32_t KJ = 0x04000400u << J;
+            nw[0] |= nsig[0] & KJ; nw[1] |= nsig[1] & KJ; nw[2] |= nsig[2] & KJ; nw[3] |= nsig[3] & KJ;
           }
         }
         if (AUX && aux_on) {
@@ -593,15 +606,16 @@ uavsim_step_tile_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
       dup0 += __shfl_xor_sync(0xffffffffu, dup0, 1); dup1 += __shfl_xor_sync(0xffffffffu, dup1, 1);
       tt0 += __shfl_xor_sync(0xffffffffu, tt0, 2); tt1 += __shfl_xor_sync(0xffffffffu, tt1, 2);
       dup0 += __shfl_xor_sync(0xffffffffu, dup0, 2); dup1 += __shfl_xor_sync(0xffffffffu, dup1, 2);
-      S.sums[r0][q] = ct1[0] + ct1[1];       // q = 0..3: sum of x, y, vx, vy over the observed targets
-      S.sums[r1][q] = ct1[2] + ct1[3];
-      S.sums[r0][8 + q] = cc1[0] + cc1[1];   // sum of x, y, cos, sin over the communication partners
-      S.sums[r1][8 + q] = cc1[2] + cc1[3];
+      // quad q holds columns 2q, 2q+1 of the accumulators: {x hi, y hi}, {x lo, y lo}, {f2 hi, f3 hi}, {f2 lo, f3 lo}
+      *reinterpret_cast<float2 *>(&S.sums[r0][2 * q]) = make_float2(ct1[0], ct1[1]);
+      *reinterpret_cast<float2 *>(&S.sums[r1][2 * q]) = make_float2(ct1[2], ct1[3]);
+      *reinterpret_cast<float2 *>(&S.sums[r0][8 + 2 * q]) = make_float2(cc1[0], cc1[1]);
+      *reinterpret_cast<float2 *>(&S.sums[r1][8 + 2 * q]) = make_float2(cc1[2], cc1[3]);
       if (q == 0) {
-        *reinterpret_cast<float4 *>(&S.sums[r0][4]) = make_float4(ct2[0], tt0, dup0, 0.f);
-        *reinterpret_cast<float4 *>(&S.sums[r1][4]) = make_float4(ct2[2], tt1, dup1, 0.f);
-        *reinterpret_cast<float2 *>(&S.sums[r0][12]) = make_float2(cc2[0], cc2[1]);
-        *reinterpret_cast<float2 *>(&S.sums[r1][12]) = make_float2(cc2[2], cc2[3]);
+        *reinterpret_cast<float4 *>(&S.sums[r0][16]) = make_float4(ct2[0], tt0, dup0, 0.f);
+        *reinterpret_cast<float4 *>(&S.sums[r1][16]) = make_float4(ct2[2], tt1, dup1, 0.f);
+        *reinterpret_cast<float2 *>(&S.sums[r0][20]) = make_float2(cc2[0], cc2[1]);
+        *reinterpret_cast<float2 *>(&S.sums[r1][20]) = make_float2(cc2[2], cc2[3]);
       }
       {  // coverage: OR over the rows of this warp; bit (10 + J) of half h of covA / covB = column 16 J + 2 q (+ 8) + h
         const uint32_t ca = ((covA >> 10) & 0xFu) | ((covA >> 22) & 0xF0u), cb = ((covB >> 10) & 0xFu) | ((covB >> 22) & 0xF0u);
@@ -614,7 +628,7 @@ uavsim_step_tile_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
         for (int J = 0; J < 4; J++) {
 #pragma unroll
           for (int kk = 0; kk < 4; kk++) {
-            const uint32_t two = ((nbrbits >> (4 * J + kk)) & 1u) | (((nbrbits >> (16 + 4 * J + kk)) & 1u) << 1);
+            const uint32_t two = ((nw[kk] >> (10 + J)) & 1u) | (((nw[kk] >> (26 + J)) & 1u) << 1);
             const int col = 16 * J + 2 * q + 8 * (kk >> 1);
             if (kk & 1) w1[col >> 5] |= two << (col & 31); else w0[col >> 5] |= two << (col & 31);
           }
@@ -645,10 +659,12 @@ uavsim_step_tile_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
       if (!slow) {
         const float chf = S.nfe[t].c, shf = S.nfe[t].s;
         const float2 ol = S.own[t];
-        const float4 st = *reinterpret_cast<const float4 *>(&S.sums[t][0]);
-        const float4 s4 = *reinterpret_cast<const float4 *>(&S.sums[t][4]);
-        const float4 sc = *reinterpret_cast<const float4 *>(&S.sums[t][8]);
-        const float2 s12 = *reinterpret_cast<const float2 *>(&S.sums[t][12]);
+        const float4 ta = *reinterpret_cast<const float4 *>(&S.sums[t][0]), tb4 = *reinterpret_cast<const float4 *>(&S.sums[t][4]);
+        const float4 ca = *reinterpret_cast<const float4 *>(&S.sums[t][8]), cb4 = *reinterpret_cast<const float4 *>(&S.sums[t][12]);
+        const float4 s4 = *reinterpret_cast<const float4 *>(&S.sums[t][16]);
+        const float2 s12 = *reinterpret_cast<const float2 *>(&S.sums[t][20]);
+        const float4 st = make_float4(ta.x + ta.z, ta.y + ta.w, tb4.x + tb4.z, tb4.y + tb4.w);   // hi + lo
+        const float4 sc = make_float4(ca.x + ca.z, ca.y + ca.w, cb4.x + cb4.z, cb4.y + cb4.w);
         if (s4.x > 0.5f) {
           const float rk = sf_rcp(s4.x);
           o5 = (fmaf(st.x, rk, -xf) - ol.x) * inv_dp_f;
@@ -702,7 +718,12 @@ uavsim_step_tile_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
         bpn = (fminf(fmaxf(bp, -0.5f), 0.0f) + 0.5f) * 2.0f - 1.0f;
         raw = fmaf(P.alpha_f, ttn, fmaf(P.beta_f, bpn, P.gamma_f * dupn));
         S.raw[t] = raw;
-        S.braw[t] = make_uint4(tl_split(raw), 0x00003C00u, 0u, 0u);
+        {  // B row of the neighbour mean: {raw hi, scale, raw lo, 0, ...} times the factor of the UAV's column tile
+          const float sc = tl_nscale(t >> 4);
+          uint4 br = make_uint4(0u, 0u, 0u, 0u);
+          tl_split2(raw * sc, sc, br.x, br.y);
+          S.braw[t] = br;
+        }
       }
       float *ob = s_obs + t * 12;
       reinterpret_cast<float4 *>(ob)[0] = make_float4(o0, o1, o2, o3);
@@ -753,19 +774,20 @@ uavsim_step_tile_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
         if (!pmi_pending) st_r += (double)r;
       }
     } else {
-      // neighbour mean as one more masked sum: weights rebuilt from the neighbour bits x {raw hi, raw lo, 1}
+      // neighbour mean as one more masked sum: the neighbour bits of column tile J, read as fp16, x {raw hi, 1, raw lo} x scale
       float cr[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int J = 0; J < 4; J++) {
+        const uint32_t KJ = 0x04000400u << J;
         uint32_t a[4];
 #pragma unroll
-        for (int kk = 0; kk < 4; kk++) a[kk] = ((nbrbits >> (4 * J + kk)) & 0x00010001u) * 0x3C00u;
+        for (int kk = 0; kk < 4; kk++) a[kk] = nw[kk] & KJ;
         uint32_t b0, b1;
         tl_ldb2(sf_smem(S.braw) + (uint32_t)J * 256u + ldm_row, b0, b1);
         tl_mma(cr, a, b0, b1);
       }
-      // thread q = 0 of a quad holds {sum raw hi, sum raw lo}, thread q = 1 the count (column 2)
-      const float cnt0 = __shfl_sync(0xffffffffu, cr[0], (lane & ~3) | 1), cnt1 = __shfl_sync(0xffffffffu, cr[2], (lane & ~3) | 1);
+      // thread q = 0 of a quad holds {sum raw hi, count}, thread q = 1 {sum raw lo, 0}
+      const float lo0 = __shfl_sync(0xffffffffu, cr[0], (lane & ~3) | 1), lo1 = __shfl_sync(0xffffffffu, cr[2], (lane & ~3) | 1);
       if (q == 0) {
         const float cf = (float)coop;
 #pragma unroll
@@ -773,7 +795,7 @@ uavsim_step_tile_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
           const int row = rr ? r1 : r0;
           const float rw = S.raw[row];
           // the UAV itself (distance 0) is in the set: taken out of sum and count
-          const float s = (rr ? (cr[2] + cr[3]) : (cr[0] + cr[1])) - rw, cnt = (rr ? cnt1 : cnt0) - 1.0f;
+          const float s = (rr ? (cr[2] + lo1) : (cr[0] + lo0)) - rw, cnt = (rr ? cr[3] : cr[1]) - 1.0f;
           float r = (cnt > 0.5f) ? fmaf(1.0f - cf, rw, cf * s * sf_rcp(cnt)) : 0.0f;
           r = fminf(fmaxf(r, -1.0f), 1.0f);
           s_rew[row] = r;

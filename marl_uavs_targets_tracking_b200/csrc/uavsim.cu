@@ -180,6 +180,26 @@ static int uavsim_create_impl(const UavSimParams *p, int64_t n_envs, int64_t env
     if (rf > k.rmax) rf = k.rmax;
     k.r_fast = (float)rf;
     k.r_tile = (float)(rf < 4096.0 ? rf : 4096.0);
+    // tile kernel: band centre / half width per radius at two swarm extents (the guard grows with the extent)
+    const double cmax = k.cx > k.cy ? k.cx : k.cy;
+    const double rr[2] = {1.3 * cmax < k.r_tile ? 1.3 * cmax : (double)k.r_tile, (double)k.r_tile};
+    for (int lv = 0; lv < 2; lv++) {
+      auto band = [&](const GuardK &G, float &C, float &H) {
+        const double gd = ((double)G.c1 * rr[lv] + (double)G.c0) * (1.0 + 1e-6);
+        const double hi = (double)G.t2_up + gd, lo = (double)G.t2_dn - gd;
+        C = (float)(0.5 * (hi + lo));
+        // |fl(s) - C| <= H must hold for every s in [lo, hi]: half the width, the rounding of C and of the subtraction
+        const double hw = 0.5 * (hi - lo) + 2.4e-7 * fabs(hi) + fabs((double)C - 0.5 * (hi + lo));
+        H = nextafterf((float)hw, INFINITY);
+        if ((double)H < hw) H = nextafterf(H, INFINITY);
+      };
+      k.tb[lv].r = (float)rr[lv];
+      if ((double)k.tb[lv].r > rr[lv]) k.tb[lv].r = nextafterf(k.tb[lv].r, 0.f);
+      band(k.g_dp, k.tb[lv].Cp, k.tb[lv].Hp);
+      band(k.g_2dp, k.tb[lv].Cd, k.tb[lv].Hd);
+      band(k.g_dc, k.tb[lv].Cc, k.tb[lv].Hc);
+      k.tb[lv].pad = 0.f;
+    }
   }
   k.dp_f = (float)p->dp; k.inv_dp_f = (float)k.inv_dp; k.inv_dc_f = (float)k.inv_dc; k.inv_na_f = (float)k.inv_na;
   k.tt_hi_f = (float)k.tt_hi; k.inv_tt_hi_f = (float)k.inv_tt_hi; k.dup_lo_f = (float)k.dup_lo; k.inv_dup_span_f = (float)k.inv_dup_span;
@@ -571,10 +591,10 @@ static bool fast_path_usable(const uavsim_t *h) {
 static int launch_step_range(uavsim_t *h, int mode, double coop, int64_t e0, int64_t cnt, int done_flag, cudaStream_t st) {
   if (fast_path_usable(h)) {
     const int v = (h->buf.obs_mask || h->buf.tracker_cnt) ? 1 : 0;
-    if (h->step_path == 2) {  // per-UAV candidate walks (kept for comparison)
+    if (h->step_path != 3) {  // per-UAV candidate walks (the default: faster than the tiles once the swarm has spread)
       const int grid = (int)(cnt < h->fast_grid_max[v] ? cnt : h->fast_grid_max[v]);
       h->fast_fn[v]<<<grid, FAST_NT, h->smem_fast[v], st>>>(h->kp, h->buf, h->d_act, e0, cnt, mode, coop, done_flag, h->d_stats);
-    } else {                  // all-pairs tiles
+    } else {                  // all-pairs tiles on the tensor path
       const int grid = (int)(cnt < h->tile_grid_max[v] ? cnt : h->tile_grid_max[v]);
       h->tile_fn[v]<<<grid, TILE_NT, h->smem_tile[v], st>>>(h->kp, h->buf, h->d_act, e0, cnt, mode, coop, done_flag, h->d_stats);
     }

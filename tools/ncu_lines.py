@@ -28,14 +28,23 @@ start = next(i for i, ln in enumerate(dis) if ln.startswith(".text.") and a.kern
 # helpers (inline PTX wrappers, intrinsics headers, fast_math) carry their own line: attribute them to the most recent
 # line of the kernel body instead (nvdisasm gives no inlined-at chain)
 main_src = open(os.path.join(os.path.dirname(os.path.abspath(a.so)), a.file)).read().splitlines()
-body_lo = next((i + 1 for i, l in enumerate(main_src) if "__device__ __noinline__ void fast_agent_exact" in l or "__global__" in l), 1)
-MARKERS = [("exact path (fp64 row)", "__device__ __noinline__ void fast_agent_exact"), ("kernel prologue", "__global__ void"),
+body_lo = next((i + 1 for i, l in enumerate(main_src) if "__device__ __noinline__ void" in l or "__global__" in l), 1)
+MARKERS_FAST = [("exact path (fp64 row)", "__device__ __noinline__ void fast_agent_exact"), ("kernel prologue", "__global__ void"),
            ("loop top: waits", "for (int64_t k = blockIdx.x"), ("phase 0a targets", "// ---- phase 0a"), ("phase 0b UAVs", "// ---- phase 0b"),
            ("phase 1 setup / guards", "// ---- phase 1"), ("targets: prefilter + walk", "// -- targets:"),
            ("UAV prefilter (2 radii)", "// -- UAV partners"), ("communication walk", "// -- communication partners"),
            ("duplicate / neighbour walk", "// -- duplicate-tracking"), ("exact call / masks / coverage", "if (exact) {"),
            ("obs, boundary, normalise", "double raw, ttn, bpn, dupn;"), ("phase 2 cooperative reward", "// ---- phase 2"),
            ("output stores", "asm volatile(\"fence.proxy.async.shared::cta;\""), ("epilogue", "// outputs complete before the CTA retires")]
+MARKERS_TILE = [("pair fix-up (fp64)", "__device__ __noinline__ void tile_fix"), ("exact path (fp64 row)", "__device__ __noinline__ void tile_agent_exact"),
+           ("kernel prologue", "__global__ void"), ("loop top: waits", "for (int64_t k = blockIdx.x"),
+           ("phase 0a targets", "// ---- phase 0a"), ("phase 0b UAVs", "// ---- phase 0b"), ("phase 0 tail: radius, barrier, next loads", "if (!(rabs == rabs))"),
+           ("phase 1 setup: bands, rows", "// ================= phase 1"), ("target tiles", "// ---- targets:"),
+           ("UAV tiles: distances + communication", "// ---- UAV partners"), ("UAV tiles: duplicate / neighbours", "// duplicate tracking / neighbours on the new-new"),
+           ("pair-phase epilogue (sums, coverage)", "// ---- hand the sums"), ("finish the UAVs", "// ================= finish the UAVs"),
+           ("cooperative reward", "// ================= cooperative reward"),
+           ("output stores", "asm volatile(\"fence.proxy.async.shared::cta;\""), ("epilogue", "// outputs complete before the CTA retires")]
+MARKERS = MARKERS_TILE if "tile" in a.file else MARKERS_FAST
 regions = []
 for name, key in MARKERS:
     ln_ = next((i + 1 for i, l in enumerate(main_src) if key in l), None)
