@@ -226,6 +226,7 @@ def main():
     run_case("s64_mean_s42", args.out, mods, cfg(64, 64), "mean", 200, 42)
     run_case("s64_self_s3", args.out, mods, cfg(64, 64), "self", 60, 3)
     run_case("s64_pmi_s42", args.out, mods, cfg(64, 64), "pmi", 30, 42)
+    run_case("s64_pmi_s9_long", args.out, mods, cfg(64, 64), "pmi", 200, 9)   # a whole MAAC-R episode of the scaled swarm
     run_case("s32_pmi_s5", args.out, mods, cfg(32, 32), "pmi", 80, 5)
     # ragged / degenerate sizes
     run_case("n1_m1_mean", args.out, mods, cfg(1, 1), "mean", 50, 11)
