@@ -373,12 +373,12 @@ __device__ __noinline__ void sf_comm_checked(const FastSmem<N, M, AUX> *Sp, cons
 }
 struct DupOut { float dup; uint32_t nbE, nbO, dpE, dpO; };
 template <int N, int M, bool AUX>
-__device__ __noinline__ void sf_dup_checked(const FastSmem<N, M, AUX> *Sp, const WalkOwn W, float T2_lo, float Tp_lo,
-                                            float Tp_hi, double s_2dp_le, double s_dp_le, float k_ex0, float k_ex1,
-                                            uint32_t cdE, uint32_t cdO, DupOut *O) {
+__device__ __noinline__ void sf_dup_checked(const FastSmem<N, M, AUX> *Sp, const WalkOwn W, float T2_lo, float T2_hi,
+                                            float Tp_lo, float Tp_hi, double s_2dp_le, double s_dp_le, float k_ex0,
+                                            float k_ex1, uint32_t cdE, uint32_t cdO, DupOut *O) {
   const FastSmem<N, M, AUX> &S = *Sp;
   float dup = 0;
-  uint32_t nb[2] = {0, 0}, dp[2] = {cdE, cdO};
+  uint32_t nb[2] = {0, 0}, dp[2] = {0, 0};
   for (int par = 0; par < 2; par++) {
     uint32_t w = par ? cdO : cdE;
     const unsigned char *rec = reinterpret_cast<const unsigned char *>(S.slotn) + 4 * par;
@@ -389,10 +389,9 @@ __device__ __noinline__ void sf_dup_checked(const FastSmem<N, M, AUX> *Sp, const
       const float *r = reinterpret_cast<const float *>(rec + 48 * b);
       const float dx = r[0] - W.xf, dy = r[2] - W.yf;
       const float s = fmaf(dx, dx, dy * dy);
-      if (s > T2_lo && !(sf_exact_pair(S.oux[2 * b + par], S.ouy[2 * b + par], W.xi, W.yi, s_2dp_le, s_2dp_le) & 1)) {
-        dp[par] ^= bit;
-        continue;
-      }
+      if (s > T2_hi) continue;  // (cdE / cdO hold every partner of the walked slots)
+      if (s > T2_lo && !(sf_exact_pair(S.oux[2 * b + par], S.ouy[2 * b + par], W.xi, W.yi, s_2dp_le, s_2dp_le) & 1)) continue;
+      dp[par] |= bit;
       dup += fast_ex2f(fmaf(fast_sqrtf(s), k_ex1, k_ex0));
       if (s <= Tp_hi) {
         bool in = true;
@@ -621,30 +620,37 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
         }
       }
 
-      // -- UAV partners: prefilter on the NEW positions against (i) the communication radius widened by one move
-      //    (a partner that moves after this UAV is tested at its old position, at most dt*v from the new one) and
-      //    (ii) the duplicate-tracking radius 2 dp.  The own bit is always set (distance 0): the own slot is walked
-      //    like any other and the own contribution, known in closed form, is taken out afterwards.
-      uint32_t ccE, ccO, cdE, cdO;
-      prefilter64<true, (int)sizeof(SlotRec)>(S.slotn, xf, yf, Tf_hi, T2_hi, ccE, ccO, cdE, cdO);
+      // -- UAV partners.  ONE prefilter on the NEW positions against the widest radius any UAV-UAV test can reach:
+      //    the communication radius widened by one move (a partner that moves after this UAV is tested at its old
+      //    position, at most dt*v from the new one) or the duplicate-tracking radius 2 dp, whichever is larger
+      //    (KParams::g_pf).  The own bit is always set (distance 0): the own slot is walked like any other and the own
+      //    contributions, known in closed form, are taken out afterwards.
+      uint32_t ccE, ccO, d0_, d1_;
+      prefilter64<false, (int)sizeof(SlotRec)>(S.slotn, xf, yf, Tf_hi, 0.f, ccE, ccO, d0_, d1_);
       const unsigned char *slot_new = reinterpret_cast<const unsigned char *>(S.slotn);
-      // -- communication partners (uav.py:124-147), two per slot.  Weights 1 / 0 from the upper guard; the largest
-      //    accepted squared distance tells afterwards whether an accepted pair sat inside the band (a partner of the
-      //    slot that the prefilter had excluded is either outside the upper guard or, by the guard's construction,
-      //    inside the band).
+      // -- ONE walk over the candidate slots, two partners per trip, for the three UAV-UAV lists:
+      //    communication (uav.py:124-147; the partner's record after its move if it moved first, before it otherwise),
+      //    duplicate-tracking punishment (uav.py:214-229) and the neighbour set (uav.py:305), both at NEW positions.
+      //    Weights 1 / 0 from the upper guards; per list the largest accepted squared distance tells afterwards
+      //    whether an accepted pair sat inside the band.  (Until round 2 the duplicate / neighbour list had its own
+      //    prefilter radius and its own walk, one partner per trip: 27 trips of 22 instructions on top of the 20
+      //    communication trips; here it rides on the communication trips for +20 instructions each.)
       {
-        uint64_t sx = 0, sy = 0, sc = 0, ss = 0, sa = 0, cn = 0;
-        float smax_c = 0.f;
+        uint64_t sx = 0, sy = 0, sc = 0, ss = 0, sa = 0, cn = 0, dp2 = 0;
+        float smax_c = 0.f, smax_d = 0.f, smax_n = 0.f;
+        const uint64_t kx1 = pack2(k_ex1, k_ex1), kx0 = pack2(k_ex0, k_ex0);
         uint32_t w = ccE | ccO;
 #pragma unroll 1
         while (w) {
           const int b = sf_msb(w);
           const uint32_t bit = 1u << b;
           w ^= bit;
-          const unsigned char *rp = slot_new + ((b < ihx) ? 0u : OLD_OFF) + 48 * b;
+          const unsigned char *rn = slot_new + 48 * b;
+          const unsigned char *rp = rn + ((b < ihx) ? 0u : OLD_OFF);
           const ulonglong2 p = *reinterpret_cast<const ulonglong2 *>(rp);         // {x0, x1}, {y0, y1}
           const ulonglong2 hd = *reinterpret_cast<const ulonglong2 *>(rp + 16);   // {cos0, cos1}, {sin0, sin1}
           const uint64_t aa = *reinterpret_cast<const uint64_t *>(rp + 32);       // {a0, a1}
+          const ulonglong2 pn = *reinterpret_cast<const ulonglong2 *>(rn);        // positions after the move
           const uint64_t dx = f2_sub(p.x, xf2), dy = f2_sub(p.y, yf2);
           const uint64_t s2 = f2_fma(dx, dx, f2_mul(dy, dy));
           const float s0 = f2_lo(s2), s1 = f2_hi(s2);
@@ -657,6 +663,19 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
           sa = f2_fma(wh, aa, sa);
           cn = f2_add(cn, wh);
           if (AUX) { if (h0) cmE |= bit; if (h1) cmO |= bit; }
+          // duplicate tracking / neighbours at the new positions
+          const uint64_t ex = f2_sub(pn.x, xf2), ey = f2_sub(pn.y, yf2);
+          const uint64_t n2 = f2_fma(ex, ex, f2_mul(ey, ey));
+          const float n0 = f2_lo(n2), n1 = f2_hi(n2);
+          const bool g0 = n0 <= T2_hi, g1 = n1 <= T2_hi;
+          const uint64_t wg = pack2(g0 ? 1.0f : 0.0f, g1 ? 1.0f : 0.0f);
+          if (g0) smax_d = fmaxf(smax_d, n0);
+          if (g1) smax_d = fmaxf(smax_d, n1);
+          const uint64_t arg = f2_fma(pack2(fast_sqrtf(n0), fast_sqrtf(n1)), kx1, kx0);
+          dp2 = f2_fma(wg, pack2(fast_ex2f(f2_lo(arg)), fast_ex2f(f2_hi(arg))), dp2);  // exp((2dp - d)/(2dp))
+          if (AUX) { if (g0) dpE |= bit; if (g1) dpO |= bit; }
+          if (n0 <= Tp_hi) { nbE |= bit; smax_n = fmaxf(smax_n, n0); }
+          if (n1 <= Tp_hi) { nbO |= bit; smax_n = fmaxf(smax_n, n1); }
         }
         // own entry of the own slot: the record that was read there (new if this UAV sits in the odd place, else old)
         // (the own entry also went into smax_c: its distance is 0 or one move, far from the band unless dt*v ~ dc; the
@@ -688,34 +707,15 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
         } else {
           o0 = o1 = o2 = o3 = o4 = -1.f;
         }
-      }
-      // -- duplicate-tracking punishment (uav.py:214-229) and the neighbour set (uav.py:305), all at NEW positions.
-      //    One partner per trip: with two MUFU per partner and two radii to flag, a slot trip cost twice a single one.
-      {
-        float dup = 0, smax_d = 0.f, smax_n = 0.f;
-        cdE &= ~(ic ? 0u : (1u << ih)); cdO &= ~(ic ? (1u << ih) : 0u);  // never its own partner
-        if (AUX) { dpE = cdE; dpO = cdO; }
-#pragma unroll
-        for (int par = 0; par < 2; par++) {
-          uint32_t w = par ? cdO : cdE, nbits = 0;
-          const unsigned char *rec = slot_new + 4 * par;
-#pragma unroll 1
-          while (w) {
-            const int b = sf_msb(w);
-            const uint32_t bit = 1u << b;
-            w ^= bit;
-            const float *r = reinterpret_cast<const float *>(rec + 48 * b);
-            const float dx = r[0] - xf, dy = r[2] - yf;
-            const float s = fmaf(dx, dx, dy * dy);
-            smax_d = fmaxf(smax_d, s);  // every candidate is accepted
-            dup += fast_ex2f(fmaf(fast_sqrtf(s), k_ex1, k_ex0));  // exp((2dp - d)/(2dp))
-            if (s <= Tp_hi) { nbits |= bit; smax_n = fmaxf(smax_n, s); }
-          }
-          if (par) nbO = nbits; else nbE = nbits;
-        }
+        // the UAV itself (distance 0 after the move) went through the duplicate / neighbour tests: taken out again
+        const uint32_t ownE = ic ? 0u : (1u << ih), ownO = ic ? (1u << ih) : 0u;
+        float dup = (f2_lo(dp2) + f2_hi(dp2)) - fast_ex2f(fmaf(fast_sqrtf(0.f), k_ex1, k_ex0));
+        nbE &= ~ownE; nbO &= ~ownO;
+        if (AUX) { dpE &= ~ownE; dpO &= ~ownO; }
         if ((smax_d > T2_lo) || (smax_n > Tp_lo)) {  // a pair inside a guard band: this list once more, checked
           DupOut X;
-          sf_dup_checked<N, M, AUX>(&S, WO, T2_lo, Tp_lo, Tp_hi, P.s_2dp_le, P.s_dp_le, k_ex0, k_ex1, cdE, cdO, &X);
+          sf_dup_checked<N, M, AUX>(&S, WO, T2_lo, T2_hi, Tp_lo, Tp_hi, P.s_2dp_le, P.s_dp_le, k_ex0, k_ex1, (ccE | ccO) & ~ownE,
+                                    (ccE | ccO) & ~ownO, &X);
           dup = X.dup; nbE = X.nbE; nbO = X.nbO;
           if (AUX) { dpE = X.dpE; dpO = X.dpO; }
         }
