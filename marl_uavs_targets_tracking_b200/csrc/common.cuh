@@ -99,10 +99,14 @@ struct uavsim {
   size_t smem_step;
   // fast step kernel (64 x 64): [0] plain, [1] with masks / per-target counts
   bool has_fast;
-  int step_path;            // 0 auto, 1 generic kernel, 2 per-UAV fast kernel, 3 tile kernel (2, 3: error if unusable)
+  int step_path;            // 0 auto, 1 generic kernel, 2 per-UAV fast kernel, 3 tile kernel, 4 small-swarm kernel (2-4: error if unusable)
   FastKernelFn fast_fn[2];
   size_t smem_fast[2];
   int fast_grid_max[2];
+  // small-swarm step kernel (n, m <= 16, step_small_kernel.cuh): groups of environments in two-warp CTAs
+  bool has_small;
+  FastKernelFn small_fn[2];
+  int small_grid_max[2];
   // tile step kernel (64 x 64, step_tile_kernel.cuh): [0] plain, [1] with masks / per-target counts
   FastKernelFn tile_fn[2];
   size_t smem_tile[2];

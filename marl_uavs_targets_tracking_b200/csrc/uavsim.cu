@@ -19,6 +19,7 @@
 #include "pmi_tc_kernel.cuh"
 #include "step_fast_kernel.cuh"
 #include "step_tile_kernel.cuh"
+#include "step_small_kernel.cuh"
 #include "aux_kernels.cuh"
 #include "replay.cuh"
 
@@ -290,7 +291,21 @@ static int uavsim_create_impl(const UavSimParams *p, int64_t n_envs, int64_t env
       if (h->tile_grid_max[v] > h->grid_max) h->grid_max = h->tile_grid_max[v];
     }
   }
+  // small-swarm kernel (step_small_kernel.cuh): groups of environments in two-warp CTAs
+  h->has_small = (k.n <= SMALL_MAX && k.m <= SMALL_MAX);
+  int small_warps = 0;
+  if (h->has_small) {
+    h->small_fn[0] = uavsim_step_small_kernel<false>;
+    h->small_fn[1] = uavsim_step_small_kernel<true>;
+    for (int v = 0; v < 2; v++) {
+      int o = 1;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, h->small_fn[v], SMALL_NT, 0));
+      h->small_grid_max[v] = h->sm_count * (o < 1 ? 1 : o);
+      if (h->small_grid_max[v] > small_warps) small_warps = h->small_grid_max[v];
+    }
+  }
   h->stat_slots = h->grid_max > 4096 ? h->grid_max : 4096;
+  if (small_warps > h->stat_slots) h->stat_slots = small_warps;  // one statistics slot per CTA of that kernel too
   CUDA_TRY(cudaMalloc(&h->d_stats, sizeof(double) * 2 * h->stat_slots * STAT_W));
   CUDA_TRY(cudaMalloc(&h->d_stats8, sizeof(double) * 8));
   CUDA_TRY(cudaMallocHost(&h->h_stats8, sizeof(double) * 8));
@@ -506,8 +521,9 @@ extern "C" int uavsim_set_pmi_path(uavsim_t *h, int path) {
 }
 
 extern "C" int uavsim_set_step_path(uavsim_t *h, int path) {
-  if (!h || path < 0 || path > 3) { SET_ERR("uavsim_set_step_path: bad argument"); return UAVSIM_ERR_ARG; }
-  if (path >= 2 && !h->has_fast) { SET_ERR("uavsim_set_step_path: the fast step kernels serve 64 x 64 swarms only"); return UAVSIM_ERR_UNSUPPORTED; }
+  if (!h || path < 0 || path > 4) { SET_ERR("uavsim_set_step_path: bad argument"); return UAVSIM_ERR_ARG; }
+  if ((path == 2 || path == 3) && !h->has_fast) { SET_ERR("uavsim_set_step_path: the fast step kernels serve 64 x 64 swarms only"); return UAVSIM_ERR_UNSUPPORTED; }
+  if (path == 4 && !h->has_small) { SET_ERR("uavsim_set_step_path: the small-swarm step kernel serves n_uav, m_targets <= %d", SMALL_MAX); return UAVSIM_ERR_UNSUPPORTED; }
   h->step_path = path;
   return 0;
 }
@@ -579,7 +595,7 @@ extern "C" int uavsim_set_pmi_weights(uavsim_t *h, const UavSimPmiWeights *w, vo
 
 // The fast kernel moves whole arrays with bulk copies: every bound array it touches must be 16-byte aligned.
 static bool fast_path_usable(const uavsim_t *h) {
-  if (!h->has_fast || h->step_path == 1) return false;
+  if (!h->has_fast || h->step_path == 1 || h->step_path == 4) return false;
   const UavSimBuffers &b = h->buf;
   const void *ptrs[] = {b.ux, b.uy, b.uh, b.ua, b.tx, b.ty, b.th, b.actions, b.obs, b.rew4};
   for (const void *q : ptrs)
@@ -589,7 +605,13 @@ static bool fast_path_usable(const uavsim_t *h) {
 
 // one step over the env range [e0, e0+cnt) on stream st
 static int launch_step_range(uavsim_t *h, int mode, double coop, int64_t e0, int64_t cnt, int done_flag, cudaStream_t st) {
-  if (fast_path_usable(h)) {
+  if (h->has_small && (h->step_path == 0 || h->step_path == 4)) {  // groups of environments in two-warp CTAs
+    const int v = (h->buf.obs_mask || h->buf.tracker_cnt) ? 1 : 0;
+    const int G = small_group(h->kp.n, h->kp.m);
+    const int64_t groups = (cnt + G - 1) / G;
+    const int grid = (int)(groups < h->small_grid_max[v] ? groups : h->small_grid_max[v]);
+    h->small_fn[v]<<<grid, SMALL_NT, 0, st>>>(h->kp, h->buf, h->d_act, e0, cnt, mode, coop, done_flag, h->d_stats);
+  } else if (fast_path_usable(h)) {
     const int v = (h->buf.obs_mask || h->buf.tracker_cnt) ? 1 : 0;
     if (h->step_path != 3) {  // per-UAV candidate walks (the default: faster than the tiles once the swarm has spread)
       const int grid = (int)(cnt < h->fast_grid_max[v] ? cnt : h->fast_grid_max[v]);
@@ -599,7 +621,7 @@ static int launch_step_range(uavsim_t *h, int mode, double coop, int64_t e0, int
       h->tile_fn[v]<<<grid, TILE_NT, h->smem_tile[v], st>>>(h->kp, h->buf, h->d_act, e0, cnt, mode, coop, done_flag, h->d_stats);
     }
   } else {
-    if (h->step_path >= 2) { SET_ERR("uavsim_step: the fast step kernel needs 64 x 64 swarms and 16-byte aligned buffers"); return UAVSIM_ERR_UNSUPPORTED; }
+    if (h->step_path >= 2) { SET_ERR("uavsim_step: the selected step kernel cannot serve this shape / these buffers (64 x 64 kernels need 16-byte aligned arrays)"); return UAVSIM_ERR_UNSUPPORTED; }
     const int64_t ngroups = (cnt + h->epb - 1) / h->epb;
     const int grid = (int)(ngroups < h->grid_max ? ngroups : h->grid_max);
     h->step_fn[h->buf.obs_mask ? 1 : 0]<<<grid, h->nt, h->smem_step, st>>>(h->kp, h->buf, h->d_dth, e0, cnt, h->epb, mode, coop, done_flag, h->d_stats);
