@@ -80,6 +80,9 @@ struct ActEntry;
 typedef void (*FastKernelFn)(const KParams, const UavSimBuffers, const ActEntry *, int64_t, int64_t, int, double, int,
                              double *);
 
+typedef void (*SmallKernelFn)(const KParams, const UavSimBuffers, const ActEntry *, int64_t, int64_t, int, double, int,
+                              double *, int, uint64_t, uint32_t);
+
 struct PmiTcDev;
 
 struct uavsim {
@@ -105,7 +108,7 @@ struct uavsim {
   int fast_grid_max[2];
   // small-swarm step kernel (n, m <= 16, step_small_kernel.cuh): groups of environments in two-warp CTAs
   bool has_small;
-  FastKernelFn small_fn[2];
+  SmallKernelFn small_fn[2];
   int small_grid_max[2];
   // tile step kernel (64 x 64, step_tile_kernel.cuh): [0] plain, [1] with masks / per-target counts
   FastKernelFn tile_fn[2];

@@ -60,7 +60,8 @@ __host__ __device__ inline int small_group(int n, int m) {
 template <bool AUX>
 __global__ void __launch_bounds__(SMALL_NT, SMALL_CTAS_PER_SM)
 uavsim_step_small_kernel(const KParams P, const UavSimBuffers B, const ActEntry *__restrict__ act_tab, int64_t env_begin,
-                         int64_t env_count, int mode, double coop, int done_flag, double *__restrict__ stats_partial) {
+                         int64_t env_count, int mode, double coop, int done_flag, double *__restrict__ stats_partial,
+                         int rng_on, uint64_t rng_seed, uint32_t rng_step) {
   __shared__ SmallSmem S;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = P.n, m = P.m, G = small_group(n, m);
@@ -69,11 +70,18 @@ uavsim_step_small_kernel(const KParams P, const UavSimBuffers B, const ActEntry 
   const bool pmi_pending = (mode == UAVSIM_MODE_PMI) && (coop != 0.0);
   const bool mean_mode = (mode == UAVSIM_MODE_MEAN) && (coop != 0.0);
   const bool aux_on = AUX && (B.obs_mask != nullptr);
-  const int gu = lane / n, iu = lane - gu * n;   // (environment of the group, UAV) of this lane
-  const int gt = lane / m, jt = lane - gt * m;   // (environment of the group, target) of this lane in warp 1, phase 0
+  // (environment of the group, UAV) of this lane, and (environment, target) in warp 1's phase 0.  lane < 32 and n, m <= 16:
+  // the quotient through one fp32 multiplication is exact
+  const int gu = (int)(((float)lane + 0.5f) * __frcp_rn((float)n)), iu = lane - gu * n;
+  const int gt = (int)(((float)lane + 0.5f) * __frcp_rn((float)m)), jt = lane - gt * m;
   const float k_ex0 = 1.4426950408889634f, k_ex1 = P.k_ex1_f;
   double st_r = 0, st_tt = 0, st_bp = 0, st_dup = 0, st_cov = 0, st_envs = 0;
   int st_cmax = 0;
+  // Programmatic dependent launch: when the steps of a rollout are queued back to back (uavsim_run_random_policy) this
+  // grid may start while its predecessor drains -- everything above (parameters, lane roles) overlaps the predecessor's
+  // tail; nothing below touches global memory before the predecessor has completed.  A plain launch passes straight through.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
     const int64_t e0 = env_begin + grp * G;
@@ -91,7 +99,15 @@ uavsim_step_small_kernel(const KParams P, const UavSimBuffers B, const ActEntry 
     if (warp == 0) {
       if (uav_lane) {
         double x = B.ux[gi], y = B.uy[gi], h = B.uh[gi];
-        const int a_old = B.ua[gi], act = B.actions[gi];
+        const int a_old = B.ua[gi];
+        int act;
+        if (rng_on) {  // random policy drawn in place (the draw of uavsim_random_actions_kernel, aux_kernels.cuh)
+          const Philox4 rr = philox4x32_10((uint32_t)iu, UAVSIM_RNG_ACTION, (uint32_t)(P.env_id_offset + e), rng_step, rng_seed);
+          act = (int)philox_below(rr.v[0], (uint32_t)P.na);
+          B.actions[gi] = act;
+        } else {
+          act = B.actions[gi];
+        }
         double sh, ch;
         heading_sincos(h, P.sincos_tab, sh, ch);
         const float cof = (float)ch, sof = (float)sh;
@@ -289,25 +305,29 @@ uavsim_step_small_kernel(const KParams P, const UavSimBuffers B, const ActEntry 
         ob[0] = make_float4(ob0, ob1, ob2, ob3);
         ob[1] = make_float4(ob4, H.tb0, H.tb1, H.tb2);
         ob[2] = make_float4(H.tb3, (float)(xi * P.inv_dc), (float)(yi * P.inv_dc), (float)((double)ai * P.inv_na));
-        if (iu == 0) {  // one lane per environment: targets with a UAV strictly inside dp (environment.py:246-253)
-          const int c = __popc(S.cov[gu]);
-          B.covered[e] = c;
-          if (B.done) B.done[e] = done_flag;
-          st_cov += (double)c;
-          st_cmax = max(st_cmax, c);
-          st_envs += 1.0;
-        }
+      }
+      if (lane < ne) {  // one lane per environment: targets with a UAV strictly inside dp (environment.py:246-253)
+        const int c = __popc(S.cov[lane]);
+        B.covered[e0 + lane] = c;
+        if (B.done) B.done[e0 + lane] = done_flag;
+        st_cov += (double)c;
+        st_cmax = max(st_cmax, c);
+        st_envs += 1.0;
       }
     } else if (B.tracker_cnt && gt < ne) {
       B.tracker_cnt[(e0 + gt) * m + jt] = S.tcnt[gt][jt];
     }
   }
-  // episode statistics of the CTA: warp 0 holds them all; one writer per slot, fixed order
+  // episode statistics of the CTA: warp 0 holds them all (coverage on its first SMALL_G lanes); one writer per slot,
+  // fixed order
   if (warp == 0) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       st_r += __shfl_down_sync(0xffffffffu, st_r, o); st_tt += __shfl_down_sync(0xffffffffu, st_tt, o);
       st_bp += __shfl_down_sync(0xffffffffu, st_bp, o); st_dup += __shfl_down_sync(0xffffffffu, st_dup, o);
+    }
+#pragma unroll
+    for (int o = SMALL_G / 2; o > 0; o >>= 1) {
       st_cov += __shfl_down_sync(0xffffffffu, st_cov, o); st_envs += __shfl_down_sync(0xffffffffu, st_envs, o);
       st_cmax = max(st_cmax, __shfl_down_sync(0xffffffffu, st_cmax, o));
     }

@@ -604,13 +604,28 @@ static bool fast_path_usable(const uavsim_t *h) {
 }
 
 // one step over the env range [e0, e0+cnt) on stream st
-static int launch_step_range(uavsim_t *h, int mode, double coop, int64_t e0, int64_t cnt, int done_flag, cudaStream_t st) {
-  if (h->has_small && (h->step_path == 0 || h->step_path == 4)) {  // groups of environments in two-warp CTAs
+// `rng`: the small-swarm kernel can draw the random policy's actions in place (seed, step) instead of reading them
+static bool small_path_in_use(const uavsim_t *h) { return h->has_small && (h->step_path == 0 || h->step_path == 4); }
+static int launch_step_range(uavsim_t *h, int mode, double coop, int64_t e0, int64_t cnt, int done_flag, cudaStream_t st,
+                             int rng_on = 0, uint64_t rng_seed = 0, uint32_t rng_step = 0) {
+  if (small_path_in_use(h)) {  // groups of environments in two-warp CTAs
     const int v = (h->buf.obs_mask || h->buf.tracker_cnt) ? 1 : 0;
     const int G = small_group(h->kp.n, h->kp.m);
     const int64_t groups = (cnt + G - 1) / G;
     const int grid = (int)(groups < h->small_grid_max[v] ? groups : h->small_grid_max[v]);
-    h->small_fn[v]<<<grid, SMALL_NT, 0, st>>>(h->kp, h->buf, h->d_act, e0, cnt, mode, coop, done_flag, h->d_stats);
+    if (rng_on) {  // a rollout loop: let this grid be scheduled while the previous step drains (it waits before its first load)
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(SMALL_NT); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      const ActEntry *act_c = h->d_act;
+      double *stats_p = h->d_stats;
+      CUDA_TRY(cudaLaunchKernelEx(&cfg, h->small_fn[v], h->kp, h->buf, act_c, e0, cnt, mode, coop, done_flag, stats_p, rng_on, rng_seed, rng_step));
+    } else {
+      h->small_fn[v]<<<grid, SMALL_NT, 0, st>>>(h->kp, h->buf, h->d_act, e0, cnt, mode, coop, done_flag, h->d_stats, rng_on, rng_seed, rng_step);
+    }
   } else if (fast_path_usable(h)) {
     const int v = (h->buf.obs_mask || h->buf.tracker_cnt) ? 1 : 0;
     if (h->step_path != 3) {  // per-UAV candidate walks (the default: faster than the tiles once the swarm has spread)
@@ -661,6 +676,14 @@ extern "C" int uavsim_run_random_policy(uavsim_t *h, int mode, double coop, uint
   if (rc) return rc;
   if (nsteps < 0) { SET_ERR("uavsim_run_random_policy: nsteps < 0"); return UAVSIM_ERR_ARG; }
   for (int64_t k = 0; k < nsteps; k++) {
+    if (small_path_in_use(h)) {  // the draw happens inside the step kernel: one launch per step
+      CUDA_TRY(cudaSetDevice(h->device));
+      h->t++;
+      const int done = (h->hp.num_steps > 0 && h->t >= h->hp.num_steps) ? 1 : 0;
+      rc = launch_step_range(h, mode, coop, 0, h->E, done, (cudaStream_t)stream, 1, seed, (uint32_t)(first_step + k));
+      if (rc) return rc;
+      continue;
+    }
     rc = uavsim_random_actions(h, seed, first_step + k, stream);
     if (rc) return rc;
     rc = uavsim_step(h, mode, coop, stream);
