@@ -283,8 +283,8 @@ def measure_workload(torch, dist, env_cls, args, name, rank, world, device, step
     sampler = ClockSampler(device.index)
     sampler.start()  # early: nvidia-smi needs a moment to start streaming; only timed-region samples are reported
     env = env_cls(n, m, 2000, 2000, 12, n_envs=E, device=device, env_id_offset=rank * E, seed=42, num_steps=EPISODE)
-    if getattr(args, "step_path", 0) and (n, m) == (64, 64):
-        env.set_step_path(args.step_path)  # A/B timing of the 64 x 64 kernels (2: per-UAV walks, 3: all-pairs tiles)
+    if getattr(args, "step_path", 0) and ((n, m) == (64, 64)) == (args.step_path in (2, 3)):
+        env.set_step_path(args.step_path)  # A/B timing (1: generic; 64 x 64: 2 per-UAV walks, 3 all-pairs tiles; small: 4)
     env.reset(cfg)
     # random-policy actions resident in HBM: one pre-drawn [E,n] tensor per step of an episode (a short bank that
     # repeats would make every UAV fly the same few turns in a loop instead of a random walk), rebound per step
@@ -468,7 +468,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU time spent on the cpu_baseline sample")
     ap.add_argument("--trace-every", type=int, default=0, help="also report ms/step per window of this many steps")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads and the CPU baseline")
-    ap.add_argument("--step-path", type=int, default=0, help="64 x 64 step kernel: 0 default, 2 per-UAV walks, 3 all-pairs tiles")
+    ap.add_argument("--step-path", type=int, default=0, help="step kernel: 0 default, 1 generic, 2 per-UAV walks (64x64), 3 all-pairs tiles (64x64), 4 small-swarm")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
 
@@ -508,7 +508,10 @@ def main():
                 extras[name] = {"value": r["value"], "unit": "agent-steps/s", "ms_per_step": r["ms"] / r["steps"],
                                 "envs_per_gpu": r["E"], "n_uav": r["n"], "m_targets": r["m"], "method": r["method"],
                                 "device_loop": r["device_loop"],
-                                "roofline_frac": r["value"] / world * alg_bytes_per_env_step(r["n"], r["m"]) / r["n"] / (hbm_peak()[0] * 1e9)}
+                                "roofline_frac": r["value"] / world * alg_bytes_per_env_step(r["n"], r["m"]) / r["n"] / (hbm_peak()[0] * 1e9),
+                                # small batches: the Python loop above is bound by the interpreter (~19 us per call), the
+                                # rollout loop below the FFI is what the kernels deliver
+                                "roofline_frac_device_loop": r["device_loop"]["value"] / world * alg_bytes_per_env_step(r["n"], r["m"]) / r["n"] / (hbm_peak()[0] * 1e9)}
             except Exception as exc:  # noqa: BLE001
                 extras[name] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
         try:

@@ -144,8 +144,8 @@ int uavsim_set_reward_weights(uavsim_t *h, double alpha, double beta, double gam
 /* pmi argument of Environment.step / PMINetwork.inference (src/models/PMINet.py:64-72). */
 int uavsim_set_pmi_weights(uavsim_t *h, const UavSimPmiWeights *w, void *stream);
 
-/* Which kernel runs Environment.step: 0 = automatic (n_uav, m_targets <= 16: the two-warp kernel of
- * csrc/step_small_kernel.cuh; 64 x 64 swarms with 16-byte aligned buffers: the per-UAV fast kernel of
+/* Which kernel runs Environment.step: 0 = automatic (n_uav, m_targets <= 16 and a batch of at most ~2.5 waves: the
+ * two-warp kernel of csrc/step_small_kernel.cuh; 64 x 64 swarms with 16-byte aligned buffers: the per-UAV fast kernel of
  * csrc/step_fast_kernel.cuh; the generic kernel otherwise), 1 = always the generic kernel, 2 = the per-UAV fast kernel,
  * 3 = the all-pairs tile kernel of csrc/step_tile_kernel.cuh, 4 = the small-swarm kernel (2-4: an error if the kernel
  * cannot serve the shape / the bound buffers).  All kernels decide every integer output identically; the switch exists

@@ -194,3 +194,75 @@ def test_fast_path_is_refused_for_other_shapes():
         with pytest.raises(UavSimError):
             env.set_step_path(path)
     env.close()
+
+
+@pytest.mark.parametrize("n,m,method", [(10, 10, "MAAC-G"), (10, 10, "MAAC-R"), (7, 5, "MAAC-G"), (16, 16, "MAAC"),
+                                         (1, 1, "MAAC-G"), (3, 16, "MAAC-G"), (16, 2, "MAAC-R")])
+def test_small_swarm_and_generic_kernels_agree(n, m, method):
+    """The two-warp small-swarm kernel (csrc/step_small_kernel.cuh, step path 4) against the generic kernel (path 1) on
+    the same seeds: masks, per-target counts, coverage and last actions identical; for MAAC-R also the neighbour sets
+    handed to the PMI kernel (through the final reward); state to 1e-9 (different sine routines), floats tight.  Ragged
+    group sizes: E = 37 is not a multiple of any group."""
+    from marl_uavs_targets_tracking_b200 import PMINetwork, default_config
+    cfg = default_config(method, n, m)
+    pmi = None
+    if method == "MAAC-R":
+        torch.manual_seed(5)
+        pmi = PMINetwork(hidden_dim=128)
+        pmi.eval()
+    E = 37
+    envs = []
+    for path in (1, 4):
+        env = _env(n, m, cfg, E, seed=9, record_masks=True, track_counts=True)
+        env.set_step_path(path)
+        env.reset(cfg)
+        envs.append(env)
+    g, f = envs
+    for t in range(60):
+        g.random_actions(3, t)
+        f.random_actions(3, t)
+        og, rg, cg = g.step_device(cfg, pmi)
+        of, rf, cf = f.step_device(cfg, pmi)
+        assert torch.equal(cg, cf), t
+        assert torch.equal(g.tracker_counts, f.tracker_counts), t
+        for k in MASKS:
+            assert torch.equal(g.masks[k], f.masks[k]), (t, k)
+        assert max_scaled_err(of.double().cpu().numpy(), og.double().cpu().numpy()) <= TOL_TIGHT
+        assert max_scaled_err(rf.double().cpu().numpy(), rg.double().cpu().numpy()) <= TOL_TIGHT
+        sg, sf = g.get_state(), f.get_state()
+        for k in ("ux", "uy", "uh", "tx", "ty", "th"):
+            assert max_scaled_err(sf[k].cpu().numpy(), sg[k].cpu().numpy()) <= 1e-9, (t, k)
+        assert torch.equal(sg["ua"], sf["ua"])
+    a, b = g.episode_stats(), f.episode_stats()
+    assert a["covered_sum"] == b["covered_sum"] and a["covered_max"] == b["covered_max"] and a["env_steps"] == b["env_steps"]
+    for k in ("rewards", "target_tracking_reward", "boundary_punishment", "duplicate_tracking_punishment"):
+        assert abs(a[k] - b[k]) <= 1e-6 * max(1.0, abs(a[k]))
+    g.close()
+    f.close()
+
+
+def test_small_swarm_rollout_loop_draws_the_same_actions():
+    """uavsim_run_random_policy on the small-swarm kernel draws the policy inside the step kernel (one launch per step,
+    programmatic dependent launch): same Philox draws, same results as random_actions + step, step by step."""
+    from marl_uavs_targets_tracking_b200 import default_config
+    n = m = 10
+    cfg = default_config("MAAC-G", n, m)
+    E = 500
+    a = _env(n, m, cfg, E, seed=21)
+    b = _env(n, m, cfg, E, seed=21)
+    for env in (a, b):
+        env.set_step_path(4)
+        env.reset(cfg)
+    T = 25
+    for t in range(T):
+        a.random_actions(77, t)
+        oa, ra, ca = a.step_device(cfg, None)
+    ob, rb, cb = b.run_random_policy(cfg, None, 77, 0, T)
+    assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(ca, cb)
+    assert torch.equal(a.actions, b.actions)
+    sa, sb = a.get_state(), b.get_state()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    assert a.episode_stats() == b.episode_stats()
+    a.close()
+    b.close()
