@@ -567,8 +567,15 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
     uint32_t nbE = 0, nbO = 0, cvE = 0, cvO = 0;
     uint32_t ncE = 0, ncO = 0;  // targets at distance exactly dp: observed and tracked, not covered
     uint32_t cmE = 0, cmO = 0, dpE = 0, dpO = 0;  // AUX: communication / duplicate sets for the mask outputs
+#ifdef FAST_ABL_NOPAIRS
+    // profiling switch (tools/gpu_round.sh): no pair work at all -- what phase 0, the finishing code and the copies cost
+    const bool exact = false;
+    o0 = o1 = o2 = o3 = o4 = o5 = o6 = o7 = o8 = -1.f; tt_f = 0.f; dup_f = 0.f;
+    if (far_env && near_origin) {
+#else
     const bool exact = far_env || near_origin;
     if (!exact) {
+#endif
       const float g_dp = fmaf(R, P.g_dp.c1, P.g_dp.c0), g_2dp = fmaf(R, P.g_2dp.c1, P.g_2dp.c0);
       const float g_dc = fmaf(R, P.g_dc.c1, P.g_dc.c0), g_pf = fmaf(R, P.g_pf.c1, P.g_pf.c0);
       const float Tp_hi = __fadd_ru(P.g_dp.t2_up, g_dp), Tp_lo = __fadd_rd(P.g_dp.t2_dn, -g_dp);

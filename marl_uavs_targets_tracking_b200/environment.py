@@ -11,6 +11,7 @@ calls return CUDA tensors: obs [E,n,12] f32, the four reward planes [E,n] f32, c
 
 There is no CPU implementation: constructing the environment needs a CUDA device and the built library.
 """
+import contextlib
 import ctypes as C
 import os
 from math import pi
@@ -140,6 +141,13 @@ class BatchedEnvironment:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _on_device(self):
+        """Context that makes this environment's GPU current.  Entering torch.cuda.device costs several microseconds --
+        more than a small step kernel takes to queue -- so it is skipped when the device is current already."""
+        if torch.cuda.current_device() == self.device.index:
+            return contextlib.nullcontext()
+        return torch.cuda.device(self.device)
+
     def _ensure_handle(self, config):
         p = params_from_config(config, self.n_uav, self.m_targets, self.x_max, self.y_max, self.action_dim,
                                self.num_steps)
@@ -170,7 +178,7 @@ class BatchedEnvironment:
         self._ensure_handle(config)
         s = self.seed if seed is None else int(seed)
         ep_seed = (s * 0x9E3779B97F4A7C15 + self._episode * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
-        with torch.cuda.device(self.device):
+        with self._on_device():
             _cabi.check(self._lib.uavsim_reset(self._h, C.c_uint64(ep_seed), self._stream()), "uavsim_reset")
         self._episode += 1
         self._clear_traces()
@@ -181,7 +189,7 @@ class BatchedEnvironment:
         for dst, src in ((self._ux, ux), (self._uy, uy), (self._uh, uh), (self._ua, ua), (self._tx, tx),
                          (self._ty, ty), (self._th, th)):
             dst.copy_(torch.as_tensor(np.asarray(src) if not torch.is_tensor(src) else src).reshape(dst.shape).to(dst.dtype))
-        with torch.cuda.device(self.device):
+        with self._on_device():
             _cabi.check(self._lib.uavsim_begin_episode(self._h, self._stream()), "uavsim_begin_episode")
         self._clear_traces()
 
@@ -241,7 +249,7 @@ class BatchedEnvironment:
         w.w0, w.b0, w.w1, w.b1, w.w2 = (f[k].ctypes.data for k in ("w0", "b0", "w1", "b1", "w2"))
         w.b2 = f["b2"]
         self._ensure_pmi_scratch()
-        with torch.cuda.device(self.device):
+        with self._on_device():
             _cabi.check(self._lib.uavsim_set_pmi_weights(self._h, C.byref(w), self._stream()), "uavsim_set_pmi_weights")
         if getattr(self, "_pmi_path", 0):
             _cabi.check(self._lib.uavsim_set_pmi_path(self._h, self._pmi_path), "uavsim_set_pmi_path")
@@ -275,7 +283,7 @@ class BatchedEnvironment:
         mode, coop = self._mode(config, pmi)
         if actions is not None:
             self._actions.copy_(actions.reshape(self._actions.shape), non_blocking=True)
-        with torch.cuda.device(self.device):
+        with self._on_device():
             _cabi.check(self._lib.uavsim_step(self._h, mode, coop, self._stream()), "uavsim_step")
         self._host = None
         return self._obs, self._rew4, self._covered
@@ -288,7 +296,7 @@ class BatchedEnvironment:
             raise UavSimError("step before reset")
         self._sync_weights(config)
         mode, coop = self._mode(config, pmi)
-        with torch.cuda.device(self.device):
+        with self._on_device():
             _cabi.check(self._lib.uavsim_run_random_policy(self._h, mode, coop, C.c_uint64(seed), int(first_step),
                                                            int(nsteps), self._stream()), "uavsim_run_random_policy")
         self._host = None
@@ -301,7 +309,7 @@ class BatchedEnvironment:
         self._sync_weights(config)
         mode, coop = self._mode(config, pmi)
         ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
-        with torch.cuda.device(self.device):
+        with self._on_device():
             _cabi.check(self._lib.uavsim_step_host(self._h, mode, coop, ptr(h_actions), ptr(h_obs), ptr(h_rew4),
                                                    ptr(h_covered), int(chunks), self._stream()), "uavsim_step_host")
         self._host = None
@@ -329,7 +337,7 @@ class BatchedEnvironment:
         self._bind()
 
     def random_actions(self, seed, step):
-        with torch.cuda.device(self.device):
+        with self._on_device():
             _cabi.check(self._lib.uavsim_random_actions(self._h, C.c_uint64(seed), int(step), self._stream()),
                         "uavsim_random_actions")
         return self._actions
@@ -377,7 +385,7 @@ class BatchedEnvironment:
         """Sums accumulated on the device since the last reset (what src/train.py:181-192 accumulates):
         dict with the four reward sums, covered sum / max and the number of env-steps."""
         out = (C.c_double * 8)()
-        with torch.cuda.device(self.device):
+        with self._on_device():
             _cabi.check(self._lib.uavsim_episode_stats(self._h, out, self._stream()), "uavsim_episode_stats")
         v = list(out)
         return {"rewards": v[0], "target_tracking_reward": v[1], "boundary_punishment": v[2],
