@@ -283,12 +283,14 @@ def measure_workload(torch, dist, env_cls, args, name, rank, world, device, step
     sampler = ClockSampler(device.index)
     sampler.start()  # early: nvidia-smi needs a moment to start streaming; only timed-region samples are reported
     env = env_cls(n, m, 2000, 2000, 12, n_envs=E, device=device, env_id_offset=rank * E, seed=42, num_steps=EPISODE)
-    if getattr(args, "step_path", 0) and ((n, m) == (64, 64)) == (args.step_path in (2, 3)):
-        env.set_step_path(args.step_path)  # A/B timing (1: generic; 64 x 64: 2 per-UAV walks, 3 all-pairs tiles; small: 4)
+    sp = getattr(args, "step_path", 0)
+    if sp == 1 or (sp in (2, 3) and (n, m) == (64, 64)) or (sp == 4 and max(n, m) <= 16):
+        env.set_step_path(sp)  # A/B timing (1: generic; 64 x 64: 2 per-UAV walks, 3 all-pairs tiles; small swarms: 4)
     env.reset(cfg)
     # random-policy actions resident in HBM: one pre-drawn [E,n] tensor per step of an episode (a short bank that
     # repeats would make every UAV fly the same few turns in a loop instead of a random walk), rebound per step
-    NB = min(EPISODE, steps + warmup)
+    # (the headline workload keeps a whole episode of them, 3.4 GB at 64 x 64 x 65 536, for the per-episode figure)
+    NB = EPISODE if with_e2e else min(EPISODE, steps + warmup)
     bank = torch.empty((NB, E, n), dtype=torch.int32, device=device)
     for b in range(NB):
         env.bind_actions(bank[b])

@@ -29,12 +29,15 @@ start = next(i for i, ln in enumerate(dis) if ln.startswith(".text.") and a.kern
 # line of the kernel body instead (nvdisasm gives no inlined-at chain)
 main_src = open(os.path.join(os.path.dirname(os.path.abspath(a.so)), a.file)).read().splitlines()
 body_lo = next((i + 1 for i, l in enumerate(main_src) if "__device__ __noinline__ void" in l or "__global__" in l), 1)
-MARKERS_FAST = [("exact path (fp64 row)", "__device__ __noinline__ void fast_agent_exact"), ("kernel prologue", "__global__ void"),
+MARKERS_FAST = [("exact path (fp64 row, whole-environment fallbacks)", "__device__ __noinline__ void fast_agent_exact"),
+           ("checked twins (fp64 decisions inside a guard band)", "__device__ __noinline__ void sf_targets_checked"),
+           ("kernel prologue", "__global__ void"),
            ("loop top: waits", "for (int64_t k = blockIdx.x"), ("phase 0a targets", "// ---- phase 0a"), ("phase 0b UAVs", "// ---- phase 0b"),
            ("phase 1 setup / guards", "// ---- phase 1"), ("targets: prefilter + walk", "// -- targets:"),
-           ("UAV prefilter (2 radii)", "// -- UAV partners"), ("communication walk", "// -- communication partners"),
-           ("duplicate / neighbour walk", "// -- duplicate-tracking"), ("exact call / masks / coverage", "if (exact) {"),
-           ("obs, boundary, normalise", "double raw, ttn, bpn, dupn;"), ("phase 2 cooperative reward", "// ---- phase 2"),
+           ("UAV prefilter (one radius)", "// -- UAV partners."), ("UAV walk: communication + duplicate + neighbours", "// -- ONE walk over the candidate slots"),
+           ("UAV walk epilogue (own entry, means)", "// own entry of the own slot"),
+           ("exact call / masks / coverage", "if (exact) {"),
+           ("boundary, normalise", "float raw, ttn, bpn, dupn;"), ("phase 2 cooperative reward, staging", "// ---- phase 2"),
            ("output stores", "asm volatile(\"fence.proxy.async.shared::cta;\""), ("epilogue", "// outputs complete before the CTA retires")]
 MARKERS_TILE = [("pair fix-up (fp64)", "__device__ __noinline__ void tile_fix"), ("exact path (fp64 row)", "__device__ __noinline__ void tile_agent_exact"),
            ("kernel prologue", "__global__ void"), ("loop top: waits", "for (int64_t k = blockIdx.x"),
