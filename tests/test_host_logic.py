@@ -99,3 +99,82 @@ def test_reduce_is_identity_without_process_group():
     st = {"rewards": 1.0, "target_tracking_reward": 2.0, "boundary_punishment": 3.0, "duplicate_tracking_punishment": 4.0,
           "covered_sum": 5.0, "covered_max": 6.0, "env_steps": 7.0}
     assert reduce_episode_stats(st) == st
+
+
+def _pmi_worker(rank, world, port, q):
+    """Each rank trains the same PMI network on ITS OWN data (as examples/train_maac_g.py does per rank)."""
+    import torch
+    from marl_uavs_targets_tracking_b200 import PMINetwork, default_config
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)                      # identical initial weights on every rank
+    net = PMINetwork(hidden_dim=32, b2_size=256)
+    cfg = default_config("MAAC-R")
+    cfg["pmi"].update(hidden_dim=32, b2_size=256, batch_size=64)
+    torch.manual_seed(100 + rank)             # different replay data and different draws per rank
+    data = torch.randn(40 * 10, 12)
+    losses = [net.train_pmi(cfg, data, 10) for _ in range(3)]
+    sd = {k: v.detach().cpu().numpy().copy() for k, v in net.state_dict().items()}  # (arrays: tensors would travel by fd)
+    q.put((rank, sd, losses))
+    dist.destroy_process_group()
+
+
+def test_pmi_training_keeps_one_network_across_ranks_gloo():
+    """several ranks train one policy against ONE reciprocal-reward network -- gradients are averaged before
+    every optimizer step and BatchNorm statistics after every pass, so parameters, buffers and the reported loss are
+    identical on all ranks although every rank sees its own data."""
+    import torch
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_pmi_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = {r: (sd, ls) for r, sd, ls in (q.get(timeout=180) for _ in range(2))}
+    [p.join(60) for p in procs]
+    (sd0, l0), (sd1, l1) = res[0], res[1]
+    assert l0 == l1
+    for k in sd0:
+        if k.endswith("num_batches_tracked"):
+            continue
+        assert np.array_equal(sd0[k], sd1[k]), k
+    # and the network did move
+    torch.manual_seed(0)
+    from marl_uavs_targets_tracking_b200 import PMINetwork
+    fresh = PMINetwork(hidden_dim=32, b2_size=256).state_dict()
+    assert not np.array_equal(fresh["fc1.weight"].numpy(), sd0["fc1.weight"])
+
+
+def test_actor_critic_checkpoints_have_the_reference_layout(tmp_path):
+    """BatchedActorCritic.save / load write actor/actor_weights_N.pth and critic/critic_weights_N.pth as
+    {'model_state_dict', 'optimizer_state_dict'} with the key names of the reference's FnnPolicyNet / FnnValueNet
+    (src/models/actor_critic.py:85-112, :181-200), so the files load into the reference's own classes and back."""
+    import torch
+    from marl_uavs_targets_tracking_b200.rollout import BatchedActorCritic
+    torch.manual_seed(1)
+    a = BatchedActorCritic(12, 16, 12, 1e-3, 1e-3, 0.95, "cpu", fused=False)
+    a.save(str(tmp_path), 7)
+    pa, pc = tmp_path / "actor" / "actor_weights_7.pth", tmp_path / "critic" / "critic_weights_7.pth"
+    assert pa.exists() and pc.exists()
+    ca, cc = torch.load(pa, map_location="cpu"), torch.load(pc, map_location="cpu")
+    assert set(ca) == set(cc) == {"model_state_dict", "optimizer_state_dict"}
+    assert list(ca["model_state_dict"]) == ["fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"]
+    assert list(cc["model_state_dict"]) == ["fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"]
+    try:  # where the copy of the reference exists, load the files into ITS classes
+        import baseline
+        if baseline.available():
+            ref = baseline.import_reference()
+            agent = ref.ActorCritic(state_dim=12, hidden_dim=16, action_dim=12, actor_lr=1e-3, critic_lr=1e-3, gamma=0.95,
+                                    device=torch.device("cpu"))
+            agent.load(str(pa), str(pc))
+            for k, v in a.actor.state_dict().items():
+                assert torch.equal(agent.actor.state_dict()[k], v)
+    except ImportError:
+        pass
+    torch.manual_seed(2)
+    b = BatchedActorCritic(12, 16, 12, 1e-3, 1e-3, 0.95, "cpu", fused=False)
+    assert not torch.equal(b.actor.fc1.weight, a.actor.fc1.weight)
+    b.load(str(pa), str(pc))
+    for (k, v), (_, w) in zip(a.actor.state_dict().items(), b.actor.state_dict().items()):
+        assert torch.equal(v, w), k
+    for (k, v), (_, w) in zip(a.critic.state_dict().items(), b.critic.state_dict().items()):
+        assert torch.equal(v, w), k
