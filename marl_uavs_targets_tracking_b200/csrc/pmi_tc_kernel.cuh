@@ -33,6 +33,7 @@
 // threads of a row take 64 columns each -> logit in shared memory; then softmax + mix per UAV.
 #pragma once
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 #ifndef TC_WAIT_HINT
 #define TC_WAIT_HINT 20000u
@@ -45,15 +46,35 @@
 #define TC_KC 16             // hidden units per ring stage = two MMA K-slices
 #define TC_NS 4              // stages of the operand rings
 #define TC_NCHUNK (TC_H3 / TC_KC)
+// Operand format of the 384 -> 128 GEMM.  TC_F16 = 1 (default): both operands split into fp16 hi + lo (11 + 11 mantissa bits,
+// the same budget as the TF32 split) and multiplied with kind::f16 MMAs, K = 16 per instruction: half the tensor instructions,
+// half the shared-memory operand bytes and half the tensor-memory columns of the TF32 variant (TC_F16 = 0, K = 8), for the
+// same three products hi*hi + lo*hi + hi*lo.  fc1 is pre-scaled by TC_WSCALE (a power of two, undone in the epilogue) so the
+// lo parts of the weights stay out of fp16's subnormal range.
+#ifndef TC_F16
+#define TC_F16 1
+#endif
+#if TC_F16
+#define TC_A_BYTES 4096      // one 128 x 16 fp16 weight block (hi or lo)
+#define TC_ACOLS 32u         // TMEM columns per A stage: 2 tiles x (8 hi + 8 lo), two fp16 per column
+#define TC_WSCALE 256.0f
+#else
 #define TC_A_BYTES 8192      // one 128 x 16 fp32 weight block (hi or lo)
-#define TC_STAGE_BYTES (2 * TC_A_BYTES)  // B_hi + B_lo = 16 KB
-#define TC_ACOL0 256u        // first TMEM column of the A ring
 #define TC_ACOLS 64u         // TMEM columns per A stage: 2 tiles x (16 hi + 16 lo)
+#define TC_WSCALE 1.0f
+#endif
+#define TC_STAGE_BYTES (2 * TC_A_BYTES)  // B_hi + B_lo
+#define TC_ACOL0 256u        // first TMEM column of the A ring
 #define TC_AMAX 512          // UAVs per environment group
 #define TC_PMAX 16384        // neighbour pairs per environment group (logits stay in shared memory until the softmax)
 
 // instruction descriptor: D = F32, A = B = TF32, K-major both, N = 128 (>>3 at bit 17), M = 128 (>>4 at bit 24)
+// (kind::f16: A = B = F16 is format 0)
+#if TC_F16
+#define TC_IDESC ((1u << 4) | (0u << 7) | (0u << 10) | ((TC_H >> 3) << 17) | ((128u >> 4) << 24))
+#else
 #define TC_IDESC ((1u << 4) | (2u << 7) | (2u << 10) | ((TC_H >> 3) << 17) | ((128u >> 4) << 24))
+#endif
 
 struct TcSmem {  // byte offsets inside dynamic shared memory (base is 1024-byte aligned)
   static constexpr uint32_t stage = 0;                                   // TC_NS x TC_STAGE_BYTES (fc1 chunks only)
@@ -118,7 +139,12 @@ __device__ __forceinline__ void umma_tf32_ts_p(uint32_t lead, uint32_t tmem_d, u
       "{\n\t.reg .pred p, q;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "setp.ne.b32 q, %5, 0;\n\t"
+#if TC_F16
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+#else
       "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+#endif
+
       ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(TC_IDESC), "r"(accumulate), "r"(lead)
       : "memory");
 }
@@ -128,6 +154,17 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float *v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                ::"r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
                : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t *u) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]) : "memory");
+}
+// (a, b) -> fp16 hi parts {a, b} and lo parts {a - hi(a), b - hi(b)}, packed with the lower K index in the low half
+__device__ __forceinline__ void tc_split_h2(float a, float b, uint32_t &hi2, uint32_t &lo2) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 back = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - back.x, b - back.y);
+  hi2 = *reinterpret_cast<const uint32_t *>(&h);
+  lo2 = *reinterpret_cast<const uint32_t *>(&l);
 }
 __device__ __forceinline__ void umma_commit_p(uint32_t lead, uint32_t bar) {
   asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
@@ -278,9 +315,14 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
             for (int q = 0; q < TC_SET; q++) {
               if (q < nts) {
                 const uint32_t d_tmem = u_tmem + 128u * (uint32_t)q;
+#if TC_F16
+                constexpr int KS = 1;        // one MMA consumes K = 16: the whole chunk, 8 TMEM columns of A (two fp16 each)
+#else
+                constexpr int KS = TC_KC / 8;  // one MMA consumes K = 8: 8 TMEM columns of A, two core-matrix columns of B
+#endif
 #pragma unroll
-                for (int ks = 0; ks < TC_KC / 8; ks++) {  // one MMA consumes K = 8: 8 TMEM columns of A, two core-matrix columns of B
-                  const uint32_t a_hi = u_tmem + TC_ACOL0 + TC_ACOLS * (uint32_t)s + 32u * (uint32_t)q + 8u * (uint32_t)ks, a_lo = a_hi + 16u;
+                for (int ks = 0; ks < KS; ks++) {
+                  const uint32_t a_hi = u_tmem + TC_ACOL0 + TC_ACOLS * (uint32_t)s + (TC_ACOLS / 2) * (uint32_t)q + 8u * (uint32_t)ks, a_lo = a_hi + TC_ACOLS / 4;
                   const uint64_t dbh = dbh0 + (uint64_t)(ks * 2 * (2048 >> 4)), dbl = dbl0 + (uint64_t)(ks * 2 * (2048 >> 4));
                   umma_tf32_ts_p(lead, d_tmem, a_hi, dbh, (c4 | s | ks) ? 1u : 0u);
 #ifndef TC_ABL_MMA1
@@ -350,7 +392,9 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
         //      two rows and writes them (hi and lo) into the stage's tensor-memory columns.  The three input branches
         //      (communication 5, observation 4, boundary/state 3 inputs; PMINet.py:45-58, BN folded) are unrolled
         //      so the rows stay in registers; each branch covers 8 chunks.
+#if !TC_F16
         const uint32_t a_lane = lane_base + TC_ACOL0 + 8u * (uint32_t)half;
+#endif
         auto run_chunk = [&](const int c, const uint64_t *xin, const int dim) {
           const uint32_t s = c % TC_NS, c4 = c / TC_NS;
           if (t > 0 || c4 > 0) {  // MMAs that read this stage have completed
@@ -377,6 +421,22 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
               }
               const float a00 = fmaxf(__uint_as_float((uint32_t)acc), 0.f), a01 = fmaxf(__uint_as_float((uint32_t)(acc >> 32)), 0.f);
               const float a10 = fmaxf(__uint_as_float((uint32_t)acc2), 0.f), a11 = fmaxf(__uint_as_float((uint32_t)(acc2 >> 32)), 0.f);
+#if TC_F16
+              // units (u, u') are neighbours along K: one packed fp16 pair per tile; activations beyond fp16's range are
+              // clamped (they do not occur with weights that produce finite rewards)
+              tc_split_h2(fminf(a00, 60000.f), fminf(a10, 60000.f), reinterpret_cast<uint32_t *>(h0)[e >> 1], reinterpret_cast<uint32_t *>(l0)[e >> 1]);
+              tc_split_h2(fminf(a01, 60000.f), fminf(a11, 60000.f), reinterpret_cast<uint32_t *>(h1)[e >> 1], reinterpret_cast<uint32_t *>(l1)[e >> 1]);
+            }
+            {  // this thread's 8 units = 4 columns of the stage: hi | lo of tile 0, hi | lo of tile 1
+              const uint32_t a4 = lane_base + TC_ACOL0 + 4u * (uint32_t)half + TC_ACOLS * s;
+              tmem_st4(a4, reinterpret_cast<const uint32_t *>(h0));
+              tmem_st4(a4 + 8u, reinterpret_cast<const uint32_t *>(l0));
+              if (live1) {
+                tmem_st4(a4 + 16u, reinterpret_cast<const uint32_t *>(h1));
+                tmem_st4(a4 + 24u, reinterpret_cast<const uint32_t *>(l1));
+              }
+            }
+#else
               h0[e] = tf32_rna(a00); l0[e] = tf32_rna(a00 - h0[e]);              // unit u,  tile 0
               h1[e] = tf32_rna(a01); l1[e] = tf32_rna(a01 - h1[e]);              // unit u,  tile 1
               h0[e + 1] = tf32_rna(a10); l0[e + 1] = tf32_rna(a10 - h0[e + 1]);  // unit u', tile 0
@@ -388,6 +448,7 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
               tmem_st8(a_lane + TC_ACOLS * s + 32u, h1);
               tmem_st8(a_lane + TC_ACOLS * s + 48u, l1);
             }
+#endif
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           }
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -417,7 +478,7 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
               tmem_ld32(lane_base + 128u * (uint32_t)q + (uint32_t)cb, v);
               float acc = part[q];
 #pragma unroll
-              for (int k = 0; k < 32; k++) acc = fmaf(s_w2[cb + k], fmaxf(v[k] + s_b1[cb + k], 0.f), acc);
+              for (int k = 0; k < 32; k++) acc = fmaf(s_w2[cb + k], fmaxf(fmaf(v[k], 1.0f / TC_WSCALE, s_b1[cb + k]), 0.f), acc);
               part[q] = acc;
             }
           }

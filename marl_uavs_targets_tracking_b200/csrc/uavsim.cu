@@ -563,18 +563,26 @@ extern "C" int uavsim_set_pmi_weights(uavsim_t *h, const UavSimPmiWeights *w, vo
   if (rc && H != TC_H) return rc;  // only the tensor path (hidden = 128) can take over a shape the CUDA-core kernel cannot hold
   h->has_tc = false;
   if (H == TC_H) {
-    // tensor-core path: fc1 split hi/lo (TF32) and laid out as the K-major UMMA tiles the kernel bulk-copies:
-    // chunk c, part {hi, lo}, element (unit o, input k) at float (k/4)*512 + o*4 + (k%4)
+    // tensor-core path: fc1 split hi/lo and laid out as the K-major UMMA tiles the kernel bulk-copies, chunk c, part
+    // {hi, lo}: fp16 (TC_F16, weights pre-scaled by TC_WSCALE): element (unit o, input k) at half (k/8)*1024 + o*8 + (k%8);
+    // TF32: at float (k/4)*512 + o*4 + (k%4)
     const size_t tile = TC_A_BYTES / 4, total_t = (size_t)TC_NCHUNK * 2 * tile;
     float *tiles = (float *)malloc(total_t * sizeof(float));
     for (int c = 0; c < TC_NCHUNK; c++)
       for (int o = 0; o < TC_H; o++)
         for (int kk = 0; kk < TC_KC; kk++) {
-          const float v = w->w1[(size_t)o * TC_H3 + c * TC_KC + kk];
+          const float v = w->w1[(size_t)o * TC_H3 + c * TC_KC + kk] * TC_WSCALE;
+#if TC_F16
+          const __half hi = __float2half_rn(v), lo = __float2half_rn(v - __half2float(hi));
+          const size_t e = (size_t)(kk / 8) * 1024 + (size_t)o * 8 + (kk % 8);
+          reinterpret_cast<__half *>(tiles + ((size_t)c * 2 + 0) * tile)[e] = hi;
+          reinterpret_cast<__half *>(tiles + ((size_t)c * 2 + 1) * tile)[e] = lo;
+#else
           const float hi = host_tf32_rna(v), lo = host_tf32_rna(v - hi);
           const size_t e = (size_t)(kk / 4) * 512 + (size_t)o * 4 + (kk % 4);
           tiles[((size_t)c * 2 + 0) * tile + e] = hi;
           tiles[((size_t)c * 2 + 1) * tile + e] = lo;
+#endif
         }
     if (!h->d_tc_tiles) CUDA_TRY(cudaMalloc(&h->d_tc_tiles, total_t * sizeof(float)));
     CUDA_TRY(cudaMemcpyAsync(h->d_tc_tiles, tiles, total_t * sizeof(float), cudaMemcpyHostToDevice, st));
