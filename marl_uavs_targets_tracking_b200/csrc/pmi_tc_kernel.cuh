@@ -39,8 +39,12 @@
 #define TC_WAIT_HINT 20000u
 #endif
 #define TC_SET 2             // tiles per set = accumulators in tensor memory (2 x 128 columns)
-#define TC_NP 256            // producer / epilogue threads (warps 1 .. 8): row r of both tiles x half of the units
-#define TC_NT (TC_NP + 64)   // + warp 0 = MMA issue, warp 9 = fc1 chunk loader (TMA)
+#ifndef TC_PARTS
+#define TC_PARTS 2           // producer threads per pair row: each takes 16 / TC_PARTS units of a stage and 128 / TC_PARTS accumulator
+#endif                       //   columns.  (4 was measured: issue slots 52 % -> 67 % busy, but 27 % more instructions: same time)
+#define TC_NP (128 * TC_PARTS)  // producer / epilogue threads (warps 1 .. TC_NP/32): row r of both tiles x one part of the units
+#define TC_NT (TC_NP + 64)   // + warp 0 = MMA issue, last warp = fc1 chunk loader (TMA)
+#define TC_UPT (16 / TC_PARTS)  // units of a stage per producer thread
 #define TC_H 128
 #define TC_H3 384
 #define TC_KC 16             // hidden units per ring stage = two MMA K-slices
@@ -63,6 +67,9 @@
 #define TC_ACOLS 64u         // TMEM columns per A stage: 2 tiles x (16 hi + 16 lo)
 #define TC_WSCALE 1.0f
 #endif
+#if !TC_F16 && TC_PARTS != 2
+#error "the TF32 variant keeps two producer threads per row: build it with -DTC_F16=0 -DTC_PARTS=2"
+#endif
 #define TC_STAGE_BYTES (2 * TC_A_BYTES)  // B_hi + B_lo
 #define TC_ACOL0 256u        // first TMEM column of the A ring
 #define TC_AMAX 512          // UAVs per environment group
@@ -84,8 +91,8 @@ struct TcSmem {  // byte offsets inside dynamic shared memory (base is 1024-byte
   static constexpr uint32_t off = nbr + TC_AMAX * 16;                    // uint32 [AMAX+4]
   static constexpr uint32_t logit = off + (TC_AMAX + 4) * 4;             // float [PMAX]
   static constexpr uint32_t w0 = logit + TC_PMAX * 4;                    // float [192*12]: per unit pair, bias and 5 weights interleaved
-  static constexpr uint32_t part = w0 + (TC_H3 / 2) * 12 * 4;          // float [2][128] fc2 partial dots of the second thread of a row
-  static constexpr uint32_t b1 = part + TC_SET * 128 * 4;                    // float [128]
+  static constexpr uint32_t part = w0 + (TC_H3 / 2) * 12 * 4;          // float [TC_PARTS-1][2][128] fc2 partial dots of the other threads of a row
+  static constexpr uint32_t b1 = part + (TC_PARTS - 1) * TC_SET * 128 * 4;   // float [128]
   static constexpr uint32_t w2 = b1 + TC_H * 4;                          // float [128]
   static constexpr uint32_t red = w2 + TC_H * 4;                         // double [7 per warp]
   static constexpr uint32_t bar = red + (TC_NT / 32) * 7 * 8;            // 3 x TC_NS + 2 mbarriers + tmem pointer
@@ -155,16 +162,20 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float *v) {
                ::"r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
                : "memory");
 }
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, const uint32_t *u) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(u[0]), "r"(u[1]) : "memory");
+}
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t *u) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]) : "memory");
 }
-// (a, b) -> fp16 hi parts {a, b} and lo parts {a - hi(a), b - hi(b)}, packed with the lower K index in the low half
+// (a, b) >= 0 -> fp16 hi parts {a, b} and lo parts {a - hi(a), b - hi(b)}, packed with the lower K index in the low half.
+// hi is the value truncated to 11 significant bits (one AND), so a - hi is exact and both conversions are exact up to the
+// final rounding of lo to 11 bits; .satfinite keeps an activation beyond fp16's range finite (it does not occur with weights
+// that produce finite rewards).
 __device__ __forceinline__ void tc_split_h2(float a, float b, uint32_t &hi2, uint32_t &lo2) {
-  const __half2 h = __floats2half2_rn(a, b);
-  const float2 back = __half22float2(h);
-  const __half2 l = __floats2half2_rn(a - back.x, b - back.y);
-  hi2 = *reinterpret_cast<const uint32_t *>(&h);
-  lo2 = *reinterpret_cast<const uint32_t *>(&l);
+  const float ha = __uint_as_float(__float_as_uint(a) & 0xffffe000u), hb = __uint_as_float(__float_as_uint(b) & 0xffffe000u);
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(hb), "f"(ha));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(b - hb), "f"(a - ha));
 }
 __device__ __forceinline__ void umma_commit_p(uint32_t lead, uint32_t bar) {
   asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
@@ -216,7 +227,7 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
   const int n = P.n, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool producer = warp >= 1 && warp <= TC_NP / 32;   // warp 0 = MMA issue, last warp = weight loader
   // producers: hardware warp w may only touch TMEM lanes 32*(w%4)..+31, so rows follow the warp id
-  const int row = 32 * (warp & 3) + lane, half = (warp - 1) >> 2, pt = tid - 32;
+  const int row = 32 * (warp & 3) + lane, half = (warp - 1) >> 2, pt = tid - 32;  // half: which part of the units / columns (0 .. TC_PARTS-1)
   float *s_obs = reinterpret_cast<float *>(smem + TcSmem::obs);
   double *s_raw = reinterpret_cast<double *>(smem + TcSmem::raw);
   uint64_t *s_nbr = reinterpret_cast<uint64_t *>(smem + TcSmem::nbr);
@@ -405,10 +416,10 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
           if (c < 0)
 #endif
           {
-            float h0[8], l0[8], h1[8], l1[8];
+            float h0[TC_UPT], l0[TC_UPT], h1[TC_UPT], l1[TC_UPT];
 #pragma unroll
-            for (int e = 0; e < 8; e += 2) {  // unit pair (u, u'): weights interleaved {b b' w0 w0' | w1 w1' w2 w2' | w3 w3' w4 w4'}
-              const float4 *wp = reinterpret_cast<const float4 *>(s_w0 + ((c * TC_KC + half * 8 + e) >> 1) * 12);
+            for (int e = 0; e < TC_UPT; e += 2) {  // unit pair (u, u'): weights interleaved {b b' w0 w0' | w1 w1' w2 w2' | w3 w3' w4 w4'}
+              const float4 *wp = reinterpret_cast<const float4 *>(s_w0 + ((c * TC_KC + half * TC_UPT + e) >> 1) * 12);
               const float4 q0 = wp[0], q1 = wp[1];
               uint64_t acc = tc_pack2(q0.x, q0.x), acc2 = tc_pack2(q0.y, q0.y);     // {row 0, row 1} of unit u / u'
               acc = tc_fma2(tc_pack2(q0.z, q0.z), xin[0], acc);   acc2 = tc_fma2(tc_pack2(q0.w, q0.w), xin[0], acc2);
@@ -422,19 +433,27 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
               const float a00 = fmaxf(__uint_as_float((uint32_t)acc), 0.f), a01 = fmaxf(__uint_as_float((uint32_t)(acc >> 32)), 0.f);
               const float a10 = fmaxf(__uint_as_float((uint32_t)acc2), 0.f), a11 = fmaxf(__uint_as_float((uint32_t)(acc2 >> 32)), 0.f);
 #if TC_F16
-              // units (u, u') are neighbours along K: one packed fp16 pair per tile; activations beyond fp16's range are
-              // clamped (they do not occur with weights that produce finite rewards)
-              tc_split_h2(fminf(a00, 60000.f), fminf(a10, 60000.f), reinterpret_cast<uint32_t *>(h0)[e >> 1], reinterpret_cast<uint32_t *>(l0)[e >> 1]);
-              tc_split_h2(fminf(a01, 60000.f), fminf(a11, 60000.f), reinterpret_cast<uint32_t *>(h1)[e >> 1], reinterpret_cast<uint32_t *>(l1)[e >> 1]);
+              // units (u, u') are neighbours along K: one packed fp16 pair per tile
+              tc_split_h2(a00, a10, reinterpret_cast<uint32_t *>(h0)[e >> 1], reinterpret_cast<uint32_t *>(l0)[e >> 1]);
+              tc_split_h2(a01, a11, reinterpret_cast<uint32_t *>(h1)[e >> 1], reinterpret_cast<uint32_t *>(l1)[e >> 1]);
             }
-            {  // this thread's 8 units = 4 columns of the stage: hi | lo of tile 0, hi | lo of tile 1
-              const uint32_t a4 = lane_base + TC_ACOL0 + 4u * (uint32_t)half + TC_ACOLS * s;
+            {  // this thread's TC_UPT units = TC_UPT / 2 columns of the stage: hi | lo of tile 0, hi | lo of tile 1
+              const uint32_t a4 = lane_base + TC_ACOL0 + (uint32_t)(TC_UPT / 2) * (uint32_t)half + TC_ACOLS * s;
+#if TC_UPT == 8
               tmem_st4(a4, reinterpret_cast<const uint32_t *>(h0));
               tmem_st4(a4 + 8u, reinterpret_cast<const uint32_t *>(l0));
               if (live1) {
                 tmem_st4(a4 + 16u, reinterpret_cast<const uint32_t *>(h1));
                 tmem_st4(a4 + 24u, reinterpret_cast<const uint32_t *>(l1));
               }
+#else
+              tmem_st2(a4, reinterpret_cast<const uint32_t *>(h0));
+              tmem_st2(a4 + 8u, reinterpret_cast<const uint32_t *>(l0));
+              if (live1) {
+                tmem_st2(a4 + 16u, reinterpret_cast<const uint32_t *>(h1));
+                tmem_st2(a4 + 24u, reinterpret_cast<const uint32_t *>(l1));
+              }
+#endif
             }
 #else
               h0[e] = tf32_rna(a00); l0[e] = tf32_rna(a00 - h0[e]);              // unit u,  tile 0
@@ -473,7 +492,7 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
         for (int q = 0; q < TC_SET; q++) {
           if (q == 0 || live1) {
 #pragma unroll 1
-            for (int cb = half * 64; cb < half * 64 + 64; cb += 32) {
+            for (int cb = half * (128 / TC_PARTS); cb < (half + 1) * (128 / TC_PARTS); cb += 32) {
               float v[32];
               tmem_ld32(lane_base + 128u * (uint32_t)q + (uint32_t)cb, v);
               float acc = part[q];
@@ -487,13 +506,16 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_accfree);  // this warp's rows have left tensor memory
         // combine the two halves of each row (producer-only named barrier: warps 0 and 9 are elsewhere)
-        if (half) { s_part[row] = part[0]; s_part[128 + row] = part[1]; }
+        if (half) { s_part[(half - 1) * 256 + row] = part[0]; s_part[(half - 1) * 256 + 128 + row] = part[1]; }
         asm volatile("bar.sync 1, %0;" ::"n"(TC_NP) : "memory");
         if (!half) {
 #pragma unroll
           for (int q = 0; q < TC_SET; q++) {
             const int p = (set * TC_SET + q) * 128 + row;
-            if (p < npairs) s_logit[p] = (part[q] + s_part[q * 128 + row]) + W.b2;
+            float sum = part[q];
+#pragma unroll
+            for (int h2 = 0; h2 < TC_PARTS - 1; h2++) sum += s_part[h2 * 256 + q * 128 + row];
+            if (p < npairs) s_logit[p] = sum + W.b2;
           }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(TC_NP) : "memory");
