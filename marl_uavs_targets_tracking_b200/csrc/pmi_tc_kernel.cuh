@@ -168,14 +168,21 @@ __device__ __forceinline__ void tmem_st2(uint32_t taddr, const uint32_t *u) {
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t *u) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]) : "memory");
 }
-// (a, b) >= 0 -> fp16 hi parts {a, b} and lo parts {a - hi(a), b - hi(b)}, packed with the lower K index in the low half.
-// hi is the value truncated to 11 significant bits (one AND), so a - hi is exact and both conversions are exact up to the
-// final rounding of lo to 11 bits; .satfinite keeps an activation beyond fp16's range finite (it does not occur with weights
-// that produce finite rewards).
-__device__ __forceinline__ void tc_split_h2(float a, float b, uint32_t &hi2, uint32_t &lo2) {
-  const float ha = __uint_as_float(__float_as_uint(a) & 0xffffe000u), hb = __uint_as_float(__float_as_uint(b) & 0xffffe000u);
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(hb), "f"(ha));
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(b - hb), "f"(a - ha));
+// ReLU + split of the layer-0 pre-activations of two neighbouring units (u, u') of the thread's two rows:
+// acc = {row 0, row 1} of unit u, acc2 = the same of unit u'.  hi is the value truncated to 11 significant bits (one AND), so
+// v - hi is exact, has the sign of v, and both conversions are exact up to the final rounding of lo to 11 bits.  The ReLU
+// rides on the conversions (.relu: a negative v gives hi = lo = 0); .satfinite keeps an activation beyond fp16's range finite
+// (it does not occur with weights that produce finite rewards).  Outputs: packed {u, u'} per row (lower K index in the low half).
+__device__ __forceinline__ void tc_relu_split(uint64_t acc, uint64_t acc2, uint32_t &hi_r0, uint32_t &lo_r0, uint32_t &hi_r1, uint32_t &lo_r1) {
+  const uint64_t m = 0xffffe000ffffe000ull;
+  const uint64_t h = acc & m, h2 = acc2 & m;
+  uint64_t l, l2;
+  asm("sub.f32x2 %0, %1, %2;" : "=l"(l) : "l"(acc), "l"(h));
+  asm("sub.f32x2 %0, %1, %2;" : "=l"(l2) : "l"(acc2), "l"(h2));
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi_r0) : "f"(__uint_as_float((uint32_t)h2)), "f"(__uint_as_float((uint32_t)h)));
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo_r0) : "f"(__uint_as_float((uint32_t)l2)), "f"(__uint_as_float((uint32_t)l)));
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi_r1) : "f"(__uint_as_float((uint32_t)(h2 >> 32))), "f"(__uint_as_float((uint32_t)(h >> 32))));
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo_r1) : "f"(__uint_as_float((uint32_t)(l2 >> 32))), "f"(__uint_as_float((uint32_t)(l >> 32))));
 }
 __device__ __forceinline__ void umma_commit_p(uint32_t lead, uint32_t bar) {
   asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
@@ -430,12 +437,10 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
                 acc = tc_fma2(tc_pack2(q2.x, q2.x), xin[3], acc); acc2 = tc_fma2(tc_pack2(q2.y, q2.y), xin[3], acc2);
                 if (dim > 4) { acc = tc_fma2(tc_pack2(q2.z, q2.z), xin[4], acc); acc2 = tc_fma2(tc_pack2(q2.w, q2.w), xin[4], acc2); }
               }
-              const float a00 = fmaxf(__uint_as_float((uint32_t)acc), 0.f), a01 = fmaxf(__uint_as_float((uint32_t)(acc >> 32)), 0.f);
-              const float a10 = fmaxf(__uint_as_float((uint32_t)acc2), 0.f), a11 = fmaxf(__uint_as_float((uint32_t)(acc2 >> 32)), 0.f);
 #if TC_F16
               // units (u, u') are neighbours along K: one packed fp16 pair per tile
-              tc_split_h2(a00, a10, reinterpret_cast<uint32_t *>(h0)[e >> 1], reinterpret_cast<uint32_t *>(l0)[e >> 1]);
-              tc_split_h2(a01, a11, reinterpret_cast<uint32_t *>(h1)[e >> 1], reinterpret_cast<uint32_t *>(l1)[e >> 1]);
+              tc_relu_split(acc, acc2, reinterpret_cast<uint32_t *>(h0)[e >> 1], reinterpret_cast<uint32_t *>(l0)[e >> 1],
+                            reinterpret_cast<uint32_t *>(h1)[e >> 1], reinterpret_cast<uint32_t *>(l1)[e >> 1]);
             }
             {  // this thread's TC_UPT units = TC_UPT / 2 columns of the stage: hi | lo of tile 0, hi | lo of tile 1
               const uint32_t a4 = lane_base + TC_ACOL0 + (uint32_t)(TC_UPT / 2) * (uint32_t)half + TC_ACOLS * s;
@@ -456,6 +461,8 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
 #endif
             }
 #else
+              const float a00 = fmaxf(__uint_as_float((uint32_t)acc), 0.f), a01 = fmaxf(__uint_as_float((uint32_t)(acc >> 32)), 0.f);
+              const float a10 = fmaxf(__uint_as_float((uint32_t)acc2), 0.f), a11 = fmaxf(__uint_as_float((uint32_t)(acc2 >> 32)), 0.f);
               h0[e] = tf32_rna(a00); l0[e] = tf32_rna(a00 - h0[e]);              // unit u,  tile 0
               h1[e] = tf32_rna(a01); l1[e] = tf32_rna(a01 - h1[e]);              // unit u,  tile 1
               h0[e + 1] = tf32_rna(a10); l0[e + 1] = tf32_rna(a10 - h0[e + 1]);  // unit u', tile 0
