@@ -44,12 +44,8 @@
 #endif                       //   columns.  (4 was measured: issue slots 52 % -> 67 % busy, but 27 % more instructions: same time)
 #define TC_NP (128 * TC_PARTS)  // producer / epilogue threads (warps 1 .. TC_NP/32): row r of both tiles x one part of the units
 #define TC_NT (TC_NP + 64)   // + warp 0 = MMA issue, last warp = fc1 chunk loader (TMA)
-#define TC_UPT (16 / TC_PARTS)  // units of a stage per producer thread
 #define TC_H 128
 #define TC_H3 384
-#define TC_KC 16             // hidden units per ring stage = two MMA K-slices
-#define TC_NS 4              // stages of the operand rings
-#define TC_NCHUNK (TC_H3 / TC_KC)
 // Operand format of the 384 -> 128 GEMM.  TC_F16 = 1 (default): both operands split into fp16 hi + lo (11 + 11 mantissa bits,
 // the same budget as the TF32 split) and multiplied with kind::f16 MMAs, K = 16 per instruction: half the tensor instructions,
 // half the shared-memory operand bytes and half the tensor-memory columns of the TF32 variant (TC_F16 = 0, K = 8), for the
@@ -59,14 +55,24 @@
 #define TC_F16 1
 #endif
 #if TC_F16
-#define TC_A_BYTES 4096      // one 128 x 16 fp16 weight block (hi or lo)
-#define TC_ACOLS 32u         // TMEM columns per A stage: 2 tiles x (8 hi + 8 lo), two fp16 per column
+#ifndef TC_KC
+#define TC_KC 32             // hidden units per ring stage = two K = 16 MMAs per product (16 was measured: the per-stage
+#endif                       //   hand-shake is a quarter of the producers' instructions; 32 halves it)
+#define TC_NS (TC_KC == 32 ? 3 : 4)   // stages of the operand rings (an even number of ring turns per set: 12 / 3, 24 / 4)
+#define TC_A_BYTES (128 * TC_KC * 2)  // one 128 x TC_KC fp16 weight block (hi or lo)
+#define TC_ACOLS (2u * TC_KC)         // TMEM columns per A stage: 2 tiles x (TC_KC/2 hi + TC_KC/2 lo), two fp16 per column
+#define TC_MMA_K 16
 #define TC_WSCALE 256.0f
 #else
+#define TC_KC 16             // hidden units per ring stage = two K = 8 MMAs per product
+#define TC_NS 4
 #define TC_A_BYTES 8192      // one 128 x 16 fp32 weight block (hi or lo)
 #define TC_ACOLS 64u         // TMEM columns per A stage: 2 tiles x (16 hi + 16 lo)
+#define TC_MMA_K 8
 #define TC_WSCALE 1.0f
 #endif
+#define TC_NCHUNK (TC_H3 / TC_KC)
+#define TC_UPT (TC_KC / TC_PARTS)  // units of a stage per producer thread
 #if !TC_F16 && TC_PARTS != 2
 #error "the TF32 variant keeps two producer threads per row: build it with -DTC_F16=0 -DTC_PARTS=2"
 #endif
@@ -333,11 +339,9 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
             for (int q = 0; q < TC_SET; q++) {
               if (q < nts) {
                 const uint32_t d_tmem = u_tmem + 128u * (uint32_t)q;
-#if TC_F16
-                constexpr int KS = 1;        // one MMA consumes K = 16: the whole chunk, 8 TMEM columns of A (two fp16 each)
-#else
-                constexpr int KS = TC_KC / 8;  // one MMA consumes K = 8: 8 TMEM columns of A, two core-matrix columns of B
-#endif
+                // one MMA consumes K = 16 fp16 (8 TMEM columns of A, two fp16 each) or K = 8 tf32 (8 columns), and two
+                // core-matrix columns of B either way
+                constexpr int KS = TC_KC / TC_MMA_K;
 #pragma unroll
                 for (int ks = 0; ks < KS; ks++) {
                   const uint32_t a_hi = u_tmem + TC_ACOL0 + TC_ACOLS * (uint32_t)s + (TC_ACOLS / 2) * (uint32_t)q + 8u * (uint32_t)ks, a_lo = a_hi + TC_ACOLS / 4;
@@ -444,21 +448,18 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
             }
             {  // this thread's TC_UPT units = TC_UPT / 2 columns of the stage: hi | lo of tile 0, hi | lo of tile 1
               const uint32_t a4 = lane_base + TC_ACOL0 + (uint32_t)(TC_UPT / 2) * (uint32_t)half + TC_ACOLS * s;
-#if TC_UPT == 8
-              tmem_st4(a4, reinterpret_cast<const uint32_t *>(h0));
-              tmem_st4(a4 + 8u, reinterpret_cast<const uint32_t *>(l0));
+              auto st = [](uint32_t addr, const float *v) {
+                const uint32_t *u = reinterpret_cast<const uint32_t *>(v);
+                if (TC_UPT == 16) tmem_st8(addr, v);
+                else if (TC_UPT == 8) tmem_st4(addr, u);
+                else tmem_st2(addr, u);
+              };
+              st(a4, h0);
+              st(a4 + TC_ACOLS / 4, l0);
               if (live1) {
-                tmem_st4(a4 + 16u, reinterpret_cast<const uint32_t *>(h1));
-                tmem_st4(a4 + 24u, reinterpret_cast<const uint32_t *>(l1));
+                st(a4 + TC_ACOLS / 2, h1);
+                st(a4 + 3 * TC_ACOLS / 4, l1);
               }
-#else
-              tmem_st2(a4, reinterpret_cast<const uint32_t *>(h0));
-              tmem_st2(a4 + 8u, reinterpret_cast<const uint32_t *>(l0));
-              if (live1) {
-                tmem_st2(a4 + 16u, reinterpret_cast<const uint32_t *>(h1));
-                tmem_st2(a4 + 24u, reinterpret_cast<const uint32_t *>(l1));
-              }
-#endif
             }
 #else
               const float a00 = fmaxf(__uint_as_float((uint32_t)acc), 0.f), a01 = fmaxf(__uint_as_float((uint32_t)(acc >> 32)), 0.f);
@@ -482,11 +483,11 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
           if (lane == 0) mbar_arrive(bar_aready + 8 * s);
         };
 #pragma unroll 1
-        for (int cc = 0; cc < 8; cc++) run_chunk(cc, xx, 5);
+        for (int cc = 0; cc < TC_NCHUNK / 3; cc++) run_chunk(cc, xx, 5);
 #pragma unroll 1
-        for (int cc = 8; cc < 16; cc++) run_chunk(cc, xx + 5, 4);
+        for (int cc = TC_NCHUNK / 3; cc < 2 * TC_NCHUNK / 3; cc++) run_chunk(cc, xx + 5, 4);
 #pragma unroll 1
-        for (int cc = 16; cc < 24; cc++) run_chunk(cc, xx + 9, 3);
+        for (int cc = 2 * TC_NCHUNK / 3; cc < TC_NCHUNK; cc++) run_chunk(cc, xx + 9, 3);
 
         // the rows of the next set are built while the tensor pipe drains the last stages of this one
         if (set + 1 < nsets) build_rows(set + 1);
