@@ -266,3 +266,34 @@ def test_small_swarm_rollout_loop_draws_the_same_actions():
     assert a.episode_stats() == b.episode_stats()
     a.close()
     b.close()
+
+
+def test_64x64_kernels_hand_the_same_neighbour_sets_to_the_pmi_kernel():
+    """MAAC-R at 64 x 64: the step kernels export raw rewards and neighbour bit sets, the PMI kernel finishes the reward.
+    Generic (1), per-UAV (2) and tile (3) kernels on the same seeds: final rewards within the tight tolerance, every other
+    output as in the MAAC-G comparison."""
+    from marl_uavs_targets_tracking_b200 import PMINetwork, default_config
+    n = m = 64
+    cfg = default_config("MAAC-R", n, m)
+    torch.manual_seed(11)
+    pmi = PMINetwork(hidden_dim=128)
+    pmi.eval()
+    E = 24
+    envs = []
+    for path in (1, 2, 3):
+        env = _env(n, m, cfg, E, seed=13)
+        env.set_step_path(path)
+        env.reset(cfg)
+        envs.append(env)
+    for t in range(25):
+        outs = []
+        for env in envs:
+            env.random_actions(5, t)
+            o, r, c = env.step_device(cfg, pmi)
+            outs.append((o.double().cpu().numpy(), r.double().cpu().numpy(), c.cpu().numpy()))
+        for k in (1, 2):
+            assert np.array_equal(outs[0][2], outs[k][2]), (t, k)
+            assert max_scaled_err(outs[k][0], outs[0][0]) <= TOL_TIGHT, (t, k)
+            assert max_scaled_err(outs[k][1], outs[0][1]) <= TOL_TIGHT, (t, k)
+    for env in envs:
+        env.close()
