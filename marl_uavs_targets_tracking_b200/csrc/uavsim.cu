@@ -465,6 +465,7 @@ static int pmi_launch_t(uavsim_t *h, int64_t e0, int64_t cnt, double coop, cudaS
 }
 
 // round to TF32 like cvt.rna.tf32.f32 (nearest, ties away from zero): keep 10 mantissa bits
+#if !TC_F16
 static float host_tf32_rna(float v) {
   uint32_t b;
   memcpy(&b, &v, 4);
@@ -472,6 +473,7 @@ static float host_tf32_rna(float v) {
   memcpy(&v, &b, 4);
   return v;
 }
+#endif
 
 static bool pmi_use_tensor(const uavsim_t *h) {
   if (!h->has_tc || h->pmi_path == 1) return false;
