@@ -152,8 +152,8 @@ int uavsim_set_pmi_weights(uavsim_t *h, const UavSimPmiWeights *w, void *stream)
  * for tests and A/B timing. */
 int uavsim_set_step_path(uavsim_t *h, int path);
 
-/* Which kernel evaluates the PMI MLP: 0 = automatic (tensor cores when hidden == 128 and the neighbour lists fit),
- * 1 = fp32 CUDA cores, 2 = tcgen05 tensor cores with 3xTF32 split operands (error if unsupported). */
+/* Which kernel evaluates the PMI MLP: 0 = automatic (tensor cores when hidden is 64 or 128 and the neighbour lists fit),
+ * 1 = fp32 CUDA cores, 2 = tcgen05 tensor cores with split fp16 hi + lo operands (error if unsupported). */
 int uavsim_set_pmi_path(uavsim_t *h, int path);
 
 /* Episode statistics accumulated by uavsim_step since the last reset (src/train.py:181-192):

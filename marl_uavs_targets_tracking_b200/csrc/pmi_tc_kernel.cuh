@@ -44,7 +44,7 @@
 #endif                       //   columns.  (4 was measured: issue slots 52 % -> 67 % busy, but 27 % more instructions: same time)
 #define TC_NP (128 * TC_PARTS)  // producer / epilogue threads (warps 1 .. TC_NP/32): row r of both tiles x one part of the units
 #define TC_NT (TC_NP + 64)   // + warp 0 = MMA issue, last warp = fc1 chunk loader (TMA)
-#define TC_H 128
+#define TC_H 128             // largest hidden size the kernel is instantiated for (64 and 128): sizes the shared-memory layout
 #define TC_H3 384
 // Operand format of the 384 -> 128 GEMM.  TC_F16 = 1 (default): both operands split into fp16 hi + lo (11 + 11 mantissa bits,
 // the same budget as the TF32 split) and multiplied with kind::f16 MMAs, K = 16 per instruction: half the tensor instructions,
@@ -84,9 +84,9 @@
 // instruction descriptor: D = F32, A = B = TF32, K-major both, N = 128 (>>3 at bit 17), M = 128 (>>4 at bit 24)
 // (kind::f16: A = B = F16 is format 0)
 #if TC_F16
-#define TC_IDESC ((1u << 4) | (0u << 7) | (0u << 10) | ((TC_H >> 3) << 17) | ((128u >> 4) << 24))
+#define TC_IDESC_BASE ((1u << 4) | (0u << 7) | (0u << 10) | ((128u >> 4) << 24))
 #else
-#define TC_IDESC ((1u << 4) | (2u << 7) | (2u << 10) | ((TC_H >> 3) << 17) | ((128u >> 4) << 24))
+#define TC_IDESC_BASE ((1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24))
 #endif
 
 struct TcSmem {  // byte offsets inside dynamic shared memory (base is 1024-byte aligned)
@@ -130,10 +130,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (spin > (1u << 22)) __trap();
   }
 }
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo) {
   // K-major, no swizzle: start address, LBO = 2048 B (between the two 16-byte K halves of an MMA),
   // SBO = 128 B (between 8-row groups), descriptor version 1 (Blackwell)
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(2048u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) |
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) |
          (1ull << 46);
 }
 // The MMA warp and the loader warp run their loops with all 32 lanes converged (warp-uniform control flow and operands,
@@ -147,7 +147,7 @@ __device__ __forceinline__ uint32_t elect_one() {
   return pred;
 }
 // D[tmem] (+)= A[tmem] * B[smem]: the A operand read from tensor memory (lane = row, one column per tf32 element)
-__device__ __forceinline__ void umma_tf32_ts_p(uint32_t lead, uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t accumulate) {
+__device__ __forceinline__ void umma_tf32_ts_p(uint32_t lead, uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t accumulate, uint32_t idesc) {
   asm volatile(
       "{\n\t.reg .pred p, q;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -158,7 +158,7 @@ __device__ __forceinline__ void umma_tf32_ts_p(uint32_t lead, uint32_t tmem_d, u
       "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
 #endif
 
-      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(TC_IDESC), "r"(accumulate), "r"(lead)
+      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate), "r"(lead)
       : "memory");
 }
 // registers -> tensor memory: lane l of the warp writes its 8 values to TMEM lane (quarter base + l), columns c .. c+7
@@ -233,9 +233,15 @@ struct PmiTcDev {
   float b2;
 };
 
+template <int H>   // hidden size of the PMI network: 128 (src/configs/*.yaml) or 64 (the default of PMINetwork's constructor)
 __global__ void __launch_bounds__(TC_NT, 1)
 uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, int64_t env_begin, int64_t env_count,
                      int G, double coop, double *__restrict__ stats_partial) {
+  static_assert(H == 64 || H == 128, "tensor PMI kernel: hidden size 64 or 128");
+  constexpr int H3 = 3 * H, NCHUNK = H3 / TC_KC;
+  constexpr uint32_t A_BYTES = (uint32_t)H * TC_KC * (TC_F16 ? 2 : 4);   // one H x TC_KC weight block (hi or lo)
+  constexpr uint32_t LBO = (uint32_t)H * 16u;                            // bytes between core-matrix columns along K
+  constexpr uint32_t IDESC = (TC_IDESC_BASE) | ((uint32_t)(H >> 3) << 17);
   extern __shared__ __align__(1024) unsigned char smem[];
   const int n = P.n, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool producer = warp >= 1 && warp <= TC_NP / 32;   // warp 0 = MMA issue, last warp = weight loader
@@ -257,11 +263,11 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
   const uint32_t bar_bfull = bar0, bar_aready = bar0 + 8 * TC_NS, bar_free = bar0 + 16 * TC_NS;  // [TC_NS]: one per stage
   const uint32_t bar_accfull = bar0 + 24 * TC_NS, bar_accfree = bar_accfull + 8;
 
-  for (int k = tid; k < (TC_H3 / 2) * 12; k += TC_NT) {  // unit pair j: {b, b', w0, w0', .. w4, w4'} -> three 128-bit loads
+  for (int k = tid; k < (H3 / 2) * 12; k += TC_NT) {  // unit pair j: {b, b', w0, w0', .. w4, w4'} -> three 128-bit loads
     const int u = 2 * (k / 12) + (k & 1), e = (k % 12) >> 1;
     s_w0[k] = (e == 0) ? W.b0[u] : W.w0[u * 5 + e - 1];
   }
-  for (int k = tid; k < TC_H; k += TC_NT) { s_b1[k] = W.b1[k]; s_w2[k] = W.w2[k]; }
+  for (int k = tid; k < H; k += TC_NT) { s_b1[k] = W.b1[k]; s_w2[k] = W.w2[k]; }
   if (tid == 0) {
     for (int k = 0; k < TC_NS; k++) {
       mbar_init(bar_bfull + 8 * k, 1);              // expect_tx by the loader lane + TMA bytes
@@ -284,7 +290,7 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
   // Static ring schedule: a set is TC_NCHUNK = 24 chunks and the rings have TC_NS = 4 stages, so chunk c of every set
   // uses stage c % 4 and it is that stage's (6 * set + c / 4)-th use: the mbarrier phase parity is (c / 4) & 1 in
   // every set, and all shared-memory / tensor-memory addresses are compile-time offsets from the bases.
-  static_assert(TC_NCHUNK % (2 * TC_NS) == 0, "ring schedule assumes an even number of ring turns per set");
+  static_assert(NCHUNK % (2 * TC_NS) == 0, "ring schedule assumes an even number of ring turns per set");
   uint32_t t = 0;   // sets processed so far by this CTA (phase of the accumulator barriers); same sequence in all roles
   const int64_t ngroups = (env_count + G - 1) / G;
   double st_r = 0;
@@ -326,7 +332,7 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
         const int nts = min(TC_SET, u_ntiles - set * TC_SET);
         if (t > 0) mbar_wait(bar_accfree, (t - 1) & 1);  // epilogue of the previous set done
 #pragma unroll 1
-        for (int c4 = 0; c4 < TC_NCHUNK / TC_NS; c4++) {
+        for (int c4 = 0; c4 < NCHUNK / TC_NS; c4++) {
           const uint32_t par = c4 & 1;
 #pragma unroll
           for (int s = 0; s < TC_NS; s++) {
@@ -334,22 +340,22 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
             mbar_wait(bar_bfull + 8 * s, par);   // weights have landed (shared memory)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             // B descriptors differ only in the 14-bit address field: add (byte offset >> 4) to the low word
-            const uint64_t dbh0 = umma_desc(sbase + TcSmem::stage + s * TC_STAGE_BYTES), dbl0 = dbh0 + (TC_A_BYTES >> 4);
+            const uint64_t dbh0 = umma_desc(sbase + TcSmem::stage + s * TC_STAGE_BYTES, LBO), dbl0 = dbh0 + (A_BYTES >> 4);
 #pragma unroll
             for (int q = 0; q < TC_SET; q++) {
               if (q < nts) {
-                const uint32_t d_tmem = u_tmem + 128u * (uint32_t)q;
+                const uint32_t d_tmem = u_tmem + (uint32_t)H * (uint32_t)q;
                 // one MMA consumes K = 16 fp16 (8 TMEM columns of A, two fp16 each) or K = 8 tf32 (8 columns), and two
                 // core-matrix columns of B either way
                 constexpr int KS = TC_KC / TC_MMA_K;
 #pragma unroll
                 for (int ks = 0; ks < KS; ks++) {
                   const uint32_t a_hi = u_tmem + TC_ACOL0 + TC_ACOLS * (uint32_t)s + (TC_ACOLS / 2) * (uint32_t)q + 8u * (uint32_t)ks, a_lo = a_hi + TC_ACOLS / 4;
-                  const uint64_t dbh = dbh0 + (uint64_t)(ks * 2 * (2048 >> 4)), dbl = dbl0 + (uint64_t)(ks * 2 * (2048 >> 4));
-                  umma_tf32_ts_p(lead, d_tmem, a_hi, dbh, (c4 | s | ks) ? 1u : 0u);
+                  const uint64_t dbh = dbh0 + (uint64_t)(ks * 2 * (LBO >> 4)), dbl = dbl0 + (uint64_t)(ks * 2 * (LBO >> 4));
+                  umma_tf32_ts_p(lead, d_tmem, a_hi, dbh, (c4 | s | ks) ? 1u : 0u, IDESC);
 #ifndef TC_ABL_MMA1
-                  umma_tf32_ts_p(lead, d_tmem, a_lo, dbh, 1u);
-                  umma_tf32_ts_p(lead, d_tmem, a_hi, dbl, 1u);
+                  umma_tf32_ts_p(lead, d_tmem, a_lo, dbh, 1u, IDESC);
+                  umma_tf32_ts_p(lead, d_tmem, a_hi, dbl, 1u, IDESC);
 #endif
                 }
               }
@@ -365,12 +371,12 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
       const int u_nsets = __shfl_sync(0xffffffffu, nsets, 0);
       for (int set = 0; set < u_nsets; set++, t++) {
 #pragma unroll 1
-        for (int c4 = 0; c4 < TC_NCHUNK / TC_NS; c4++) {
+        for (int c4 = 0; c4 < NCHUNK / TC_NS; c4++) {
 #pragma unroll
           for (int s = 0; s < TC_NS; s++) {
             if (t > 0 || c4 > 0) mbar_wait(bar_free + 8 * s, (c4 & 1) ^ 1);  // the MMAs of the previous use are done
             load_chunk_p(lead, sbase + TcSmem::stage + s * TC_STAGE_BYTES,
-                         W.w1_tiles + (size_t)(c4 * TC_NS + s) * (2 * TC_A_BYTES / 4), 2 * TC_A_BYTES, bar_bfull + 8 * s);
+                         W.w1_tiles + (size_t)(c4 * TC_NS + s) * (2 * A_BYTES / 4), 2 * A_BYTES, bar_bfull + 8 * s);
           }
         }
       }
@@ -483,11 +489,11 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
           if (lane == 0) mbar_arrive(bar_aready + 8 * s);
         };
 #pragma unroll 1
-        for (int cc = 0; cc < TC_NCHUNK / 3; cc++) run_chunk(cc, xx, 5);
+        for (int cc = 0; cc < NCHUNK / 3; cc++) run_chunk(cc, xx, 5);
 #pragma unroll 1
-        for (int cc = TC_NCHUNK / 3; cc < 2 * TC_NCHUNK / 3; cc++) run_chunk(cc, xx + 5, 4);
+        for (int cc = NCHUNK / 3; cc < 2 * NCHUNK / 3; cc++) run_chunk(cc, xx + 5, 4);
 #pragma unroll 1
-        for (int cc = 2 * TC_NCHUNK / 3; cc < TC_NCHUNK; cc++) run_chunk(cc, xx + 9, 3);
+        for (int cc = 2 * NCHUNK / 3; cc < NCHUNK; cc++) run_chunk(cc, xx + 9, 3);
 
         // the rows of the next set are built while the tensor pipe drains the last stages of this one
         if (set + 1 < nsets) build_rows(set + 1);
@@ -500,9 +506,9 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
         for (int q = 0; q < TC_SET; q++) {
           if (q == 0 || live1) {
 #pragma unroll 1
-            for (int cb = half * (128 / TC_PARTS); cb < (half + 1) * (128 / TC_PARTS); cb += 32) {
+            for (int cb = half * (H / TC_PARTS); cb < (half + 1) * (H / TC_PARTS); cb += 32) {
               float v[32];
-              tmem_ld32(lane_base + 128u * (uint32_t)q + (uint32_t)cb, v);
+              tmem_ld32(lane_base + (uint32_t)H * (uint32_t)q + (uint32_t)cb, v);
               float acc = part[q];
 #pragma unroll
               for (int k = 0; k < 32; k++) acc = fmaf(s_w2[cb + k], fmaxf(fmaf(v[k], 1.0f / TC_WSCALE, s_b1[cb + k]), 0.f), acc);

@@ -488,8 +488,12 @@ static int pmi_tc_launch(uavsim_t *h, int64_t e0, int64_t cnt, double coop, cuda
   const int64_t ngroups = (cnt + h->tc_g - 1) / h->tc_g;
   int grid = (int)(ngroups < h->sm_count ? ngroups : h->sm_count);
   if (grid > h->stat_slots) grid = h->stat_slots;
-  uavsim_pmi_tc_kernel<<<grid, TC_NT, TcSmem::total, st>>>(h->kp, h->buf, W, e0, cnt, h->tc_g, coop,
-                                                          h->d_stats + (size_t)h->stat_slots * STAT_W);
+  if (h->pmi.H == 64)
+    uavsim_pmi_tc_kernel<64><<<grid, TC_NT, TcSmem::total, st>>>(h->kp, h->buf, W, e0, cnt, h->tc_g, coop,
+                                                                h->d_stats + (size_t)h->stat_slots * STAT_W);
+  else
+    uavsim_pmi_tc_kernel<128><<<grid, TC_NT, TcSmem::total, st>>>(h->kp, h->buf, W, e0, cnt, h->tc_g, coop,
+                                                                 h->d_stats + (size_t)h->stat_slots * STAT_W);
   CUDA_TRY(cudaGetLastError());
   h->launches++;
   return 0;
@@ -499,7 +503,7 @@ static int pmi_launch(uavsim_t *h, int64_t e0, int64_t cnt, double coop, cudaStr
   if (!configure_only && pmi_use_tensor(h)) return pmi_tc_launch(h, e0, cnt, coop, st);
   if (!configure_only && !h->has_cc) {
     SET_ERR("PMI mode: n_uav=%d is too large for the CUDA-core PMI kernel and the tensor path is %s", h->kp.n,
-            h->pmi_path == 1 ? "switched off (uavsim_set_pmi_path 1)" : "unavailable (hidden != 128)");
+            h->pmi_path == 1 ? "switched off (uavsim_set_pmi_path 1)" : "unavailable (hidden is neither 64 nor 128)");
     return UAVSIM_ERR_UNSUPPORTED;
   }
   switch (h->pmi.H) {
@@ -515,7 +519,7 @@ static int pmi_launch(uavsim_t *h, int64_t e0, int64_t cnt, double coop, cudaStr
 extern "C" int uavsim_set_pmi_path(uavsim_t *h, int path) {
   if (!h || path < 0 || path > 2) { SET_ERR("uavsim_set_pmi_path: bad argument"); return UAVSIM_ERR_ARG; }
   if (path == 2 && h->has_pmi && !pmi_use_tensor(h) && !(h->has_tc && h->pmi_path == 1)) {
-    SET_ERR("uavsim_set_pmi_path: the tensor-core path needs hidden = 128 and n_uav*(n_uav-1) <= %d", TC_PMAX);
+    SET_ERR("uavsim_set_pmi_path: the tensor-core path needs hidden = 64 or 128 and n_uav*(n_uav-1) <= %d", TC_PMAX);
     return UAVSIM_ERR_UNSUPPORTED;
   }
   h->pmi_path = path;
@@ -562,21 +566,23 @@ extern "C" int uavsim_set_pmi_weights(uavsim_t *h, const UavSimPmiWeights *w, vo
   int rc = pmi_configure(h);
   if (!rc) rc = pmi_launch(h, 0, 0, 0.0, st, true);
   h->has_cc = rc == 0;
-  if (rc && H != TC_H) return rc;  // only the tensor path (hidden = 128) can take over a shape the CUDA-core kernel cannot hold
+  const bool tc_shape = (H == 128 || H == 64);
+  if (rc && !tc_shape) return rc;  // only the tensor path (hidden 64 / 128) can take over a shape the CUDA-core kernel cannot hold
   h->has_tc = false;
-  if (H == TC_H) {
+  if (tc_shape) {
     // tensor-core path: fc1 split hi/lo and laid out as the K-major UMMA tiles the kernel bulk-copies, chunk c, part
-    // {hi, lo}: fp16 (TC_F16, weights pre-scaled by TC_WSCALE): element (unit o, input k) at half (k/8)*1024 + o*8 + (k%8);
-    // TF32: at float (k/4)*512 + o*4 + (k%4)
-    const size_t tile = TC_A_BYTES / 4, total_t = (size_t)TC_NCHUNK * 2 * tile;
+    // {hi, lo}: fp16 (TC_F16, weights pre-scaled by TC_WSCALE): element (unit o, input k) at half (k/8)*(H*8) + o*8 + (k%8);
+    // TF32 (H = 128 only): at float (k/4)*512 + o*4 + (k%4)
+    const int H3 = 3 * H, nchunk = H3 / TC_KC;
+    const size_t tile = (size_t)H * TC_KC * (TC_F16 ? 2 : 4) / 4, total_t = (size_t)nchunk * 2 * tile;
     float *tiles = (float *)malloc(total_t * sizeof(float));
-    for (int c = 0; c < TC_NCHUNK; c++)
-      for (int o = 0; o < TC_H; o++)
+    for (int c = 0; c < nchunk; c++)
+      for (int o = 0; o < H; o++)
         for (int kk = 0; kk < TC_KC; kk++) {
-          const float v = w->w1[(size_t)o * TC_H3 + c * TC_KC + kk] * TC_WSCALE;
+          const float v = w->w1[(size_t)o * H3 + c * TC_KC + kk] * TC_WSCALE;
 #if TC_F16
           const __half hi = __float2half_rn(v), lo = __float2half_rn(v - __half2float(hi));
-          const size_t e = (size_t)(kk / 8) * 1024 + (size_t)o * 8 + (kk % 8);
+          const size_t e = (size_t)(kk / 8) * ((size_t)H * 8) + (size_t)o * 8 + (kk % 8);
           reinterpret_cast<__half *>(tiles + ((size_t)c * 2 + 0) * tile)[e] = hi;
           reinterpret_cast<__half *>(tiles + ((size_t)c * 2 + 1) * tile)[e] = lo;
 #else
@@ -586,11 +592,12 @@ extern "C" int uavsim_set_pmi_weights(uavsim_t *h, const UavSimPmiWeights *w, vo
           tiles[((size_t)c * 2 + 1) * tile + e] = lo;
 #endif
         }
-    if (!h->d_tc_tiles) CUDA_TRY(cudaMalloc(&h->d_tc_tiles, total_t * sizeof(float)));
+    if (h->d_tc_tiles) { CUDA_TRY(cudaStreamSynchronize(st)); cudaFree(h->d_tc_tiles); h->d_tc_tiles = nullptr; }
+    CUDA_TRY(cudaMalloc(&h->d_tc_tiles, total_t * sizeof(float)));
     CUDA_TRY(cudaMemcpyAsync(h->d_tc_tiles, tiles, total_t * sizeof(float), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     free(tiles);
-    rc = raise_dynamic_smem((const void *)uavsim_pmi_tc_kernel, h->device, TcSmem::total);
+    rc = raise_dynamic_smem(H == 64 ? (const void *)uavsim_pmi_tc_kernel<64> : (const void *)uavsim_pmi_tc_kernel<128>, h->device, TcSmem::total);
     if (rc) return rc;
     const int n = h->kp.n, per_env = n * (n - 1) > 0 ? n * (n - 1) : 1;
     int G = TC_AMAX / n;

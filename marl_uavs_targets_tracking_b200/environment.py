@@ -255,7 +255,7 @@ class BatchedEnvironment:
             _cabi.check(self._lib.uavsim_set_pmi_path(self._h, self._pmi_path), "uavsim_set_pmi_path")
 
     def set_pmi_path(self, path):
-        """0 = automatic, 1 = fp32 CUDA cores, 2 = tcgen05 tensor cores (3xTF32)."""
+        """0 = automatic, 1 = fp32 CUDA cores, 2 = tcgen05 tensor cores (split fp16 operands; hidden 64 or 128)."""
         self._pmi_path = int(path)
         if self._h is not None:
             _cabi.check(self._lib.uavsim_set_pmi_path(self._h, self._pmi_path), "uavsim_set_pmi_path")

@@ -1,5 +1,6 @@
-"""MAAC-R reward through both PMI kernels: fp32 CUDA cores (path 1) and tcgen05 tensor cores with 3xTF32 split
-operands (path 2), against the CPU oracle (src/agent/uav.py:262-291, src/models/PMINet.py:41-72)."""
+"""MAAC-R reward through both PMI kernels: fp32 CUDA cores (path 1) and tcgen05 tensor cores with split fp16 hi + lo
+operands (path 2; hidden sizes 128 = the shipped YAML files and 64 = the default of the reference's PMINetwork
+constructor), against the CPU oracle (src/agent/uav.py:262-291, src/models/PMINet.py:41-72)."""
 import numpy as np
 import pytest
 import torch
@@ -9,7 +10,7 @@ from gpu_util import golden_config, golden_pmi_module, max_scaled_err, oracle_pa
 
 pytestmark = pytest.mark.gpu
 TOL_PMI = 1e-5      # contract
-TOL_TC = 2e-6       # what the 3xTF32 path should achieve (fp32-class products)
+TOL_TC = 2e-6       # what the split-operand path should achieve (fp32-class products)
 
 
 def _env(n, m, cfg, E, **kw):
@@ -18,21 +19,22 @@ def _env(n, m, cfg, E, **kw):
     return BatchedEnvironment(n, m, e["x_max"], e["y_max"], e["na"], n_envs=E, device="cuda:0", **kw)
 
 
-def _pmi(seed=1):
+def _pmi(seed=1, hidden=128):
     from marl_uavs_targets_tracking_b200 import PMINetwork
     torch.manual_seed(seed)
-    pmi = PMINetwork(hidden_dim=128)
+    pmi = PMINetwork(hidden_dim=hidden)
     for bn in (pmi.bn_comm, pmi.bn_obs, pmi.bn_boundary_state, pmi.bn1):
         bn.running_mean.normal_(0, 0.3)
         bn.running_var.uniform_(0.5, 1.5)
     return pmi.eval()
 
 
+@pytest.mark.parametrize("hidden", [128, 64])
 @pytest.mark.parametrize("n,m,E,T", [(10, 10, 300, 40), (64, 64, 9, 12), (5, 3, 1, 10), (32, 32, 40, 20), (90, 4, 3, 6)])
-def test_tensor_path_matches_oracle_and_cuda_core_path(oracle, n, m, E, T):
+def test_tensor_path_matches_oracle_and_cuda_core_path(oracle, n, m, E, T, hidden):
     from marl_uavs_targets_tracking_b200 import default_config
     cfg = default_config("MAAC-R", n, m)
-    pmi = _pmi()
+    pmi = _pmi(hidden=hidden)
     envs = {}
     for path in (1, 2):
         e = _env(n, m, cfg, E, seed=21)
@@ -86,11 +88,11 @@ def test_tensor_path_unsupported_sizes_fall_back_or_fail_loudly():
     env = _env(10, 10, cfg, 8)
     env.reset(cfg)
     torch.manual_seed(0)
-    small = PMINetwork(hidden_dim=64).eval()
+    small = PMINetwork(hidden_dim=32).eval()
     env.random_actions(1, 0)
-    env.step_device(cfg, small)            # automatic: hidden 64 -> CUDA-core kernel
+    env.step_device(cfg, small)            # automatic: hidden 32 -> CUDA-core kernel
     with pytest.raises(UavSimError):
-        env.set_pmi_path(2)                # tensor path demanded but hidden != 128
+        env.set_pmi_path(2)                # tensor path demanded but hidden is neither 64 nor 128
     env.close()
 
 
