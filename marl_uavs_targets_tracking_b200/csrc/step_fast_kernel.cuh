@@ -403,19 +403,6 @@ __device__ __noinline__ void sf_dup_checked(const FastSmem<N, M, AUX> *Sp, const
   O->dup = dup; O->nbE = nb[0]; O->nbO = nb[1]; O->dpE = dp[0]; O->dpO = dp[1];
 }
 
-// sin / cos of a heading: the wrapped range takes the inline routine, anything else the library one (whose pointer
-// arguments stay inside the cold branch)
-__device__ __forceinline__ void heading_sincos(double h, const double *tab, double &s, double &c) {
-  if (fabs(h) < 3.3) {
-    double s1, c1;
-    fm_sincos_tab(h, tab, &s1, &c1);
-    s = s1; c = c1;
-  } else {
-    double s2, c2;
-    sincos_shared(h, &s2, &c2);
-    s = s2; c = c2;
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 // the kernel

@@ -25,6 +25,7 @@
 // e/2*n (error <= ~1e-7 against the 1e-5 bar).
 #pragma once
 #include "common.cuh"
+#include "fast_math.cuh"
 
 // tuning knobs (overridable with -D for experiments)
 #ifndef UAVSIM_NT64
@@ -123,6 +124,20 @@ struct EnvView {
 
 // one copy of the fp64 sincos code for both call sites (instruction-fetch footprint)
 __device__ __noinline__ void sincos_shared(double h, double *s, double *c) { sincos(h, s, c); }
+
+// sin / cos of a heading: the wrapped range takes the inline routine, anything else the library one (whose pointer
+// arguments stay inside the cold branch)
+__device__ __forceinline__ void heading_sincos(double h, const double *tab, double &s, double &c) {
+  if (fabs(h) < 3.3) {
+    double s1, c1;
+    fm_sincos_tab(h, tab, &s1, &c1);
+    s = s1; c = c1;
+  } else {
+    double s2, c2;
+    sincos_shared(h, &s2, &c2);
+    s = s2; c = c2;
+  }
+}
 
 // (h + pi) % (2 pi) - pi with Python's float % (uav.py:97).  For h + pi in [-2pi, 4pi) -- always, unless dt * rate
 // exceeds a full turn -- the fmod is one exact subtraction (Sterbenz) or, below zero, the same single addition
@@ -516,7 +531,7 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
       const EnvView V{S.env + (size_t)te * L.stride, L};
       double x = B.tx[gi], y = B.ty[gi], h = B.th[gi];
       double sh, ch;
-      sincos_shared(h, &sh, &ch);
+      heading_sincos(h, P.sincos_tab, sh, ch);  // (< 1 ulp table routine; the library call took 83 instructions per heading)
       x += P.dtv_t * ch;
       y += P.dtv_t * sh;
       // reflection (target.py:52-58); cos/sin of the reflected heading follow from the identities
@@ -544,7 +559,7 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
       double x = B.ux[gi], y = B.uy[gi], h = B.uh[gi];
       const int a_old = B.ua[gi], act = B.actions[gi];
       double sh, ch;
-      sincos_shared(h, &sh, &ch);
+      heading_sincos(h, P.sincos_tab, sh, ch);
       V.opos()[i] = make_double2(x, y); V.ohd()[i] = make_double2(ch, sh); V.oa()[i] = a_old;
       x += P.dtv_u * ch;
       y += P.dtv_u * sh;
