@@ -65,7 +65,10 @@ struct KParams {
   // fp32 copies of the constants the fast kernel's fp32 output arithmetic uses (no per-iteration conversions)
   float dp_f, inv_dp_f, inv_dc_f, inv_na_f, tt_hi_f, inv_tt_hi_f, dup_lo_f, inv_dup_span_f, alpha_f, beta_f, gamma_f;
   float k_ex1_f, tv_over_uv_f, cx_f, cy_f;
+  float dtv_u_f;  // dt*v_max of the UAVs in fp32
   const double *sincos_tab;  // [FM_TAB_SIZE][2] sine / cosine of k pi/32 (fast_math.cuh), device memory
+  int stat_slots;            // slots per region of the statistics array
+  int *fast_ctr;             // fast step kernel: {next environment beyond the first wave, CTAs that have left}, zero between launches
 };
 
 struct PmiDev {
@@ -93,7 +96,7 @@ struct uavsim {
   int device, sm_count;
   int64_t E;
   double *d_dth;      // [3*na] dt * heading-rate per action (src/agent/uav.py:73-81,96), its cos and sin
-  double *d_stats;    // [2][slots][STAT_W] per-CTA partial sums (step kernel | pmi kernel)
+  double *d_stats;    // [3][slots][STAT_W] per-CTA partial sums (step kernel | pmi kernel | fast step kernel: int64 counts of 2^-22)
   double *d_stats8;   // [8] reduced
   double *h_stats8;   // pinned
   int stat_slots;
@@ -116,6 +119,7 @@ struct uavsim {
   int tile_grid_max[2];
   ActEntry *d_act;          // [na] per action: dt * rate (fp64), cos / sin of it (fp32)
   double *d_sctab;          // sine / cosine table of the fast kernel's heading routine
+  int *d_fast_ctr;          // work counter of the fast kernel (KParams::fast_ctr)
   // pmi
   bool has_pmi;
   PmiDev pmi;
@@ -170,6 +174,21 @@ __device__ __forceinline__ int warp_max(int v) {
 
 // Block-wide reduction of per-thread statistics into this CTA's slot (accumulating across launches;
 // one writer per slot, no atomics, so the totals are reproducible for a fixed launch geometry).
+// the four reward sums of the fast step kernel as 64-bit fixed-point counts (exact, order-independent)
+__device__ inline void block_stats_commit_fx(long long *red /*smem [2][4]*/, long long *slot, long long v0, long long v1, long long v2,
+                                             long long v3) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int o = 16; o > 0; o >>= 1) {
+    v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+    v2 += __shfl_xor_sync(0xffffffffu, v2, o); v3 += __shfl_xor_sync(0xffffffffu, v3, o);
+  }
+  __syncthreads();
+  if (lane == 0 && wid < 2) { red[wid * 4 + 0] = v0; red[wid * 4 + 1] = v1; red[wid * 4 + 2] = v2; red[wid * 4 + 3] = v3; }
+  __syncthreads();
+  if (threadIdx.x < 4) slot[threadIdx.x] += red[threadIdx.x] + red[4 + threadIdx.x];
+  __syncthreads();
+}
+
 __device__ void block_stats_commit(double *red /*smem [nwarps*7], at most 64 doubles: 9 warps*/, double *slot, double v0, double v1, double v2,
                                    double v3, double v4, int vmax, double v6, int nthreads) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = nthreads >> 5;

@@ -76,6 +76,7 @@ struct __align__(128) FastSmem {
   uint32_t cover[2][2];  // per warp: targets with a UAV strictly inside dp (even / odd word)
   uint32_t rmax[2];      // per warp: largest |coordinate - centre| as float bits
   unsigned long long mbar;
+  long long next_k;      // the environment this CTA takes next (drawn from the launch-wide counter)
 };
 static_assert(sizeof(SlotRec) == 48 && sizeof(TSlot) == 32, "slot layout");
 
@@ -149,6 +150,9 @@ __device__ __forceinline__ int sf_msb(uint32_t w) {  // index of the highest set
   asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(w));
   return r;
 }
+// A value in [-1, 1] as a count of 2^-22: v + 3 lies in [2, 4], where consecutive floats are 2^-22 apart and the bit
+// pattern is linear in the value (round to nearest even).  FADD + IADD3 instead of a conversion and an fp64 add.
+__device__ __forceinline__ int sf_fx(float v) { return __float_as_int(v + 3.0f) - 0x40400000; }
 __device__ __forceinline__ float sf_rcp(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -414,6 +418,7 @@ template <int N, int M, bool AUX>
 __global__ void __launch_bounds__(FAST_NT, FAST_CTAS_PER_SM)
 uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *__restrict__ act_tab, int64_t env_begin,
                         int64_t env_count, int mode, double coop, int done_flag, double *__restrict__ stats_partial) {
+  long long *const stats_fx = reinterpret_cast<long long *>(stats_partial + 2 * (size_t)P.stat_slots * STAT_W);  // third region
   static_assert(N == 64 && M == 64 && FAST_NT == 64, "one thread per UAV and per target");
   typedef FastSmem<N, M, AUX> SmemT;
   static_assert(offsetof(SmemT, sloto) - offsetof(SmemT, slotn) == sizeof(SlotRec) * (N / 2), "record offset");
@@ -453,15 +458,24 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
   const int64_t plane = P.E * N;
   const float inv_dp_f = P.inv_dp_f, inv_dc_f = P.inv_dc_f, inv_na_f = P.inv_na_f;
   const float k_ex0 = 1.4426950408889634f, k_ex1 = P.k_ex1_f;
-  double st_r = 0, st_tt = 0, st_bp = 0, st_dup = 0, st_cov = 0, st_envs = 0;
+  // Statistics of the four reward planes as FIXED-POINT sums (2^-22 per count, FastFx): which CTA takes which
+  // environment depends on timing, and only integer sums give the same totals whatever the grouping.  Coverage and
+  // environment counts are integers in fp64 (exact in any order).
+  int fx_r = 0, fx_tt = 0, fx_bp = 0, fx_dup = 0;                 // at most 2^22 per environment
+  long long fxs_r = 0, fxs_tt = 0, fxs_bp = 0, fxs_dup = 0;
+  double st_cov = 0, st_envs = 0;
   int st_cmax = 0;
+  uint32_t trips = 0;
   uint32_t parity = 0;
   const int ih = t >> 1, ic = t & 1;   // own slot and place in it
   // Slots below ihx hold partners that moved before this UAV (their NEW records are observed), slots from ihx on
   // partners that move after it (OLD records); the own slot follows its other occupant (2 ih < t iff t is odd).
   const int ihx = ih + ic;
 
-  for (int64_t k = blockIdx.x; k < env_count; k += gridDim.x) {
+  // Environments beyond the first wave are handed out by a launch-wide counter: CTAs that the warp schedulers favour
+  // take more of them, and all CTAs of an SM finish together (with a fixed stride the resident warps thinned out over
+  // the last quarter of the launch: 24 of 28 warps per SM on average).
+  for (int64_t k = blockIdx.x, k_next = 0; k < env_count; k = k_next) {
     const int64_t e = env_begin + k;
     // The thread that committed the previous outputs waits until they have left shared memory.  (Bulk groups belong
     // to the issuing thread: elect.sync with a full mask picks the same lane every time.)
@@ -539,8 +553,12 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
       if (lane == 0) S.rmax[warp] = rm;
     }
     __syncthreads();
-    if (warp == 0 && k + gridDim.x < env_count) {  // next environment, behind the pair phase
-      if (elect_one()) issue_loads(e + gridDim.x);
+    if (warp == 0) {  // next environment, behind the pair phase
+      if (elect_one()) {
+        const int64_t kn = (int64_t)gridDim.x + (int64_t)atomicAdd(P.fast_ctr, 1);
+        S.next_k = kn;
+        if (kn < env_count) issue_loads(env_begin + kn);
+      }
     }
 
     // ---- phase 1: pair tests, observation, raw reward ----
@@ -564,7 +582,12 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
     if (!exact) {
 #endif
       const float g_dp = fmaf(R, P.g_dp.c1, P.g_dp.c0), g_2dp = fmaf(R, P.g_2dp.c1, P.g_2dp.c0);
-      const float g_dc = fmaf(R, P.g_dc.c1, P.g_dc.c0), g_pf = fmaf(R, P.g_pf.c1, P.g_pf.c0);
+      // An old position rebuilt from the new one carries the rounding of the new coordinate, of the cosine and of the
+      // FMA: at most u (2R + dt v) instead of u R, so the offset's error grows from 2uR to u (3R + dt v) <= twice the
+      // modelled one plus the guard's slope times dt v.
+      const float ndtv_f = -P.dtv_u_f;
+      const float g_dc = 2.0f * fmaf(R, P.g_dc.c1, P.g_dc.c0) + P.g_dc.c1 * fabsf(P.dtv_u_f);
+      const float g_pf = fmaf(R, P.g_pf.c1, P.g_pf.c0);
       const float Tp_hi = __fadd_ru(P.g_dp.t2_up, g_dp), Tp_lo = __fadd_rd(P.g_dp.t2_dn, -g_dp);
       const float T2_hi = __fadd_ru(P.g_2dp.t2_up, g_2dp), T2_lo = __fadd_rd(P.g_2dp.t2_dn, -g_2dp);
       const float Tc_hi = __fadd_ru(P.g_dc.t2_up, g_dc), Tc_lo = __fadd_rd(P.g_dc.t2_dn, -g_dc);
@@ -640,18 +663,26 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
           const uint32_t bit = 1u << b;
           w ^= bit;
           const unsigned char *rn = slot_new + 48 * b;
-          const unsigned char *rp = rn + ((b < ihx) ? 0u : OLD_OFF);
-          const ulonglong2 p = *reinterpret_cast<const ulonglong2 *>(rp);         // {x0, x1}, {y0, y1}
+          const bool moved = b < ihx;
+          const unsigned char *rp = rn + (moved ? 0u : OLD_OFF);
           const ulonglong2 hd = *reinterpret_cast<const ulonglong2 *>(rp + 16);   // {cos0, cos1}, {sin0, sin1}
           const uint64_t aa = *reinterpret_cast<const uint64_t *>(rp + 32);       // {a0, a1}
           const ulonglong2 pn = *reinterpret_cast<const ulonglong2 *>(rn);        // positions after the move
+          // position before the move = position after it - dt v (cos h, sin h) of the OLD heading (uav.py:88-94): two
+          // packed FMAs instead of a third 16-byte load per trip; the communication guard carries the extra rounding
+          const float mv = moved ? 0.0f : ndtv_f;
+          const uint64_t mv2 = pack2(mv, mv);
+          ulonglong2 p;
+          p.x = f2_fma(hd.x, mv2, pn.x); p.y = f2_fma(hd.y, mv2, pn.y);
           const uint64_t dx = f2_sub(p.x, xf2), dy = f2_sub(p.y, yf2);
           const uint64_t s2 = f2_fma(dx, dx, f2_mul(dy, dy));
           const float s0 = f2_lo(s2), s1 = f2_hi(s2);
           const bool h0 = s0 <= Tc_hi, h1 = s1 <= Tc_hi;
           const uint64_t wh = pack2(h0 ? 1.0f : 0.0f, h1 ? 1.0f : 0.0f);
-          if (h0) smax_c = fmaxf(smax_c, s0);
-          if (h1) smax_c = fmaxf(smax_c, s1);
+          {  // largest accepted squared distance through the weights: one packed product and one three-way maximum
+            const uint64_t sw = f2_mul(s2, wh);
+            smax_c = fmaxf(fmaxf(smax_c, f2_lo(sw)), f2_hi(sw));
+          }
           sx = f2_fma(wh, dx, sx); sy = f2_fma(wh, dy, sy);
           sc = f2_fma(wh, hd.x, sc); ss = f2_fma(wh, hd.y, ss);
           sa = f2_fma(wh, aa, sa);
@@ -663,13 +694,18 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
           const float n0 = f2_lo(n2), n1 = f2_hi(n2);
           const bool g0 = n0 <= T2_hi, g1 = n1 <= T2_hi;
           const uint64_t wg = pack2(g0 ? 1.0f : 0.0f, g1 ? 1.0f : 0.0f);
-          if (g0) smax_d = fmaxf(smax_d, n0);
-          if (g1) smax_d = fmaxf(smax_d, n1);
+          {
+            const uint64_t nw = f2_mul(n2, wg);
+            smax_d = fmaxf(fmaxf(smax_d, f2_lo(nw)), f2_hi(nw));
+          }
           const uint64_t arg = f2_fma(pack2(fast_sqrtf(n0), fast_sqrtf(n1)), kx1, kx0);
           dp2 = f2_fma(wg, pack2(fast_ex2f(f2_lo(arg)), fast_ex2f(f2_hi(arg))), dp2);  // exp((2dp - d)/(2dp))
           if (AUX) { if (g0) dpE |= bit; if (g1) dpO |= bit; }
-          if (n0 <= Tp_hi) { nbE |= bit; smax_n = fmaxf(smax_n, n0); }
-          if (n1 <= Tp_hi) { nbO |= bit; smax_n = fmaxf(smax_n, n1); }
+          {  // neighbour bits and their largest accepted squared distance through all-ones / zero masks
+            const uint32_t m0 = (n0 <= Tp_hi) ? 0xffffffffu : 0u, m1 = (n1 <= Tp_hi) ? 0xffffffffu : 0u;
+            nbE |= m0 & bit; nbO |= m1 & bit;
+            smax_n = fmaxf(fmaxf(smax_n, __uint_as_float(__float_as_uint(n0) & m0)), __uint_as_float(__float_as_uint(n1) & m1));
+          }
         }
         // own entry of the own slot: the record that was read there (new if this UAV sits in the odd place, else old)
         // (the own entry also went into smax_c: its distance is 0 or one move, far from the band unless dt*v ~ dc; the
@@ -677,7 +713,9 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
         float own_w, own_dx, own_dy, own_c, own_s, own_a;
         {
           const float *r = reinterpret_cast<const float *>(slot_new + (ic ? 0u : OLD_OFF) + 48 * ih) + ic;
-          own_dx = r[0] - xf; own_dy = r[2] - yf; own_c = r[4]; own_s = r[6]; own_a = r[8];
+          own_c = r[4]; own_s = r[6]; own_a = r[8];
+          // the same arithmetic as the walk: 0 in the odd place (new record), one move back in the even place
+          own_dx = fmaf(own_c, ic ? 0.0f : ndtv_f, xf) - xf; own_dy = fmaf(own_s, ic ? 0.0f : ndtv_f, yf) - yf;
           const float s_own = fmaf(own_dx, own_dx, own_dy * own_dy);
           own_w = sf_le(s_own, Tc_hi);
         }
@@ -767,6 +805,7 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
       S.raw[t] = raw;
     }
     __syncthreads();  // every walk is over: the slot areas become the output staging
+    k_next = S.next_k;
 
     // ---- phase 2: cooperative reward (environment.py:222-227), coverage count, outputs ----
     {
@@ -800,8 +839,12 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
       s_rew[N + t] = ttn;
       s_rew[2 * N + t] = bpn;
       s_rew[3 * N + t] = dupn;
-      if (!pmi_pending) st_r += (double)r;
-      st_tt += (double)ttn; st_bp += (double)bpn; st_dup += (double)dupn;
+      if (!pmi_pending) fx_r += sf_fx(r);
+      fx_tt += sf_fx(ttn); fx_bp += sf_fx(bpn); fx_dup += sf_fx(dupn);
+      if ((++trips & 255u) == 0u) {  // 256 environments fill 31 bits: move the sums on to 64 bits
+        fxs_r += fx_r; fxs_tt += fx_tt; fxs_bp += fx_bp; fxs_dup += fx_dup;
+        fx_r = fx_tt = fx_bp = fx_dup = 0;
+      }
       if (AUX && B.tracker_cnt) B.tracker_cnt[e * M + t] = S.tcnt[t];
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk copies
@@ -836,7 +879,13 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
   if (warp == 0) {
     if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // outputs complete before the CTA retires
   }
+  if (t == 0) {  // the last CTA to leave rewinds the counter for the next launch
+    __threadfence();
+    if (atomicAdd(P.fast_ctr + 1, 1) == (int)gridDim.x - 1) { P.fast_ctr[0] = 0; P.fast_ctr[1] = 0; __threadfence(); }
+  }
   __syncthreads();
-  block_stats_commit(reinterpret_cast<double *>(S.ux), stats_partial + (size_t)blockIdx.x * STAT_W, st_r, st_tt, st_bp,
-                     st_dup, st_cov, st_cmax, st_envs, FAST_NT);
+  fxs_r += fx_r; fxs_tt += fx_tt; fxs_bp += fx_bp; fxs_dup += fx_dup;
+  block_stats_commit_fx(reinterpret_cast<long long *>(S.ux), stats_fx + (size_t)blockIdx.x * STAT_W, fxs_r, fxs_tt, fxs_bp, fxs_dup);
+  block_stats_commit(reinterpret_cast<double *>(S.ux), stats_partial + (size_t)blockIdx.x * STAT_W, 0.0, 0.0, 0.0, 0.0, st_cov,
+                     st_cmax, st_envs, FAST_NT);
 }

@@ -207,12 +207,16 @@ static int uavsim_create_impl(const UavSimParams *p, int64_t n_envs, int64_t env
   k.alpha_f = (float)k.alpha; k.beta_f = (float)k.beta; k.gamma_f = (float)k.gamma;
   k.k_ex1_f = (float)(-1.4426950408889634 / k.two_dp); k.tv_over_uv_f = (float)k.tv_over_uv;
   k.cx_f = (float)k.cx; k.cy_f = (float)k.cy;
+  k.dtv_u_f = (float)k.dtv_u;
   {
     double tab[FM_TAB_SIZE * 2];
     fm_fill_table(tab);
     CUDA_TRY(cudaMalloc(&h->d_sctab, sizeof(tab)));
     CUDA_TRY(cudaMemcpy(h->d_sctab, tab, sizeof(tab), cudaMemcpyHostToDevice));
     k.sincos_tab = h->d_sctab;
+    CUDA_TRY(cudaMalloc(&h->d_fast_ctr, 2 * sizeof(int)));
+    CUDA_TRY(cudaMemset(h->d_fast_ctr, 0, 2 * sizeof(int)));
+    k.fast_ctr = h->d_fast_ctr;
   }
 
   // per action: dt * discrete_action(a) (src/agent/uav.py:73-81, :96) in the reference's evaluation order,
@@ -306,10 +310,11 @@ static int uavsim_create_impl(const UavSimParams *p, int64_t n_envs, int64_t env
   }
   h->stat_slots = h->grid_max > 4096 ? h->grid_max : 4096;
   if (small_warps > h->stat_slots) h->stat_slots = small_warps;  // one statistics slot per CTA of that kernel too
-  CUDA_TRY(cudaMalloc(&h->d_stats, sizeof(double) * 2 * h->stat_slots * STAT_W));
+  h->kp.stat_slots = h->stat_slots;
+  CUDA_TRY(cudaMalloc(&h->d_stats, sizeof(double) * 3 * h->stat_slots * STAT_W));
   CUDA_TRY(cudaMalloc(&h->d_stats8, sizeof(double) * 8));
   CUDA_TRY(cudaMallocHost(&h->h_stats8, sizeof(double) * 8));
-  CUDA_TRY(cudaMemset(h->d_stats, 0, sizeof(double) * 2 * h->stat_slots * STAT_W));
+  CUDA_TRY(cudaMemset(h->d_stats, 0, sizeof(double) * 3 * h->stat_slots * STAT_W));
 
   CUDA_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
@@ -326,7 +331,7 @@ static int uavsim_create_impl(const UavSimParams *p, int64_t n_envs, int64_t env
 extern "C" int uavsim_destroy(uavsim_t *h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
-  cudaFree(h->d_dth); cudaFree(h->d_act); cudaFree(h->d_sctab); cudaFree(h->d_stats); cudaFree(h->d_stats8); cudaFreeHost(h->h_stats8);
+  cudaFree(h->d_dth); cudaFree(h->d_act); cudaFree(h->d_sctab); cudaFree(h->d_fast_ctr); cudaFree(h->d_stats); cudaFree(h->d_stats8); cudaFreeHost(h->h_stats8);
   cudaFree(h->d_pmi_blob); cudaFree(h->d_tc_tiles);
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_comp) cudaStreamDestroy(h->s_comp);
@@ -371,7 +376,7 @@ static int check_bound(uavsim_t *h, const char *who) {
 }
 
 static int clear_counters(uavsim_t *h, cudaStream_t st) {
-  const int count = 2 * h->stat_slots * STAT_W;
+  const int count = 3 * h->stat_slots * STAT_W;  // (an all-zero double is an all-zero int64)
   uavsim_stats_clear_kernel<<<(count + 255) / 256, 256, 0, st>>>(h->d_stats, count);
   CUDA_TRY(cudaGetLastError());
   h->launches++;

@@ -297,3 +297,37 @@ def test_64x64_kernels_hand_the_same_neighbour_sets_to_the_pmi_kernel():
             assert max_scaled_err(outs[k][1], outs[0][1]) <= TOL_TIGHT, (t, k)
     for env in envs:
         env.close()
+
+
+def test_counter_scheduled_launch_is_reproducible_and_complete():
+    """The fast kernel hands environments beyond the first wave of CTAs out from a launch-wide counter, so which CTA
+    steps which environment depends on timing.  With more environments than resident CTAs (8 192 > 148 x 14), two runs
+    of the same seeds must still give identical outputs, identical state and IDENTICAL statistics (fixed-point sums),
+    every environment must be stepped exactly once per launch (env_steps, and the generic kernel as the witness), and
+    the counter must be back at zero for the next launch."""
+    from marl_uavs_targets_tracking_b200 import default_config
+    n = m = 64
+    cfg = default_config("MAAC-G", n, m)
+    E, T = 8192, 12
+    runs = []
+    for path in (2, 2, 1):
+        env = _env(n, m, cfg, E, seed=31)
+        env.set_step_path(path)
+        env.reset(cfg)
+        for t in range(T):
+            env.random_actions(5, t)
+            obs, rew4, cov = env.step_device(cfg, None)
+        runs.append((obs.clone(), rew4.clone(), cov.clone(), {k: v.clone() for k, v in env.get_state().items()}, env.episode_stats()))
+        env.close()
+    a, b, g = runs
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    for k in a[3]:
+        assert torch.equal(a[3][k], b[3][k]), k
+    assert a[4] == b[4], (a[4], b[4])
+    assert a[4]["env_steps"] == E * T
+    assert torch.equal(a[2], g[2]) and torch.equal(a[3]["ua"], g[3]["ua"])
+    assert max_scaled_err(a[0].double().cpu().numpy(), g[0].double().cpu().numpy()) <= TOL_TIGHT
+    assert max_scaled_err(a[1].double().cpu().numpy(), g[1].double().cpu().numpy()) <= TOL_TIGHT
+    assert a[4]["covered_sum"] == g[4]["covered_sum"] and a[4]["covered_max"] == g[4]["covered_max"]
+    for k in ("rewards", "target_tracking_reward", "boundary_punishment", "duplicate_tracking_punishment"):
+        assert abs(a[4][k] - g[4][k]) <= 1e-6 * max(1.0, abs(g[4][k])), k
