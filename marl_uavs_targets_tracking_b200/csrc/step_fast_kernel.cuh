@@ -170,10 +170,13 @@ __device__ __forceinline__ void prefilter64(const void *__restrict__ pf, float x
   const uint64_t xf2 = pack2(xf, xf), yf2 = pack2(yf, yf), nA = pack2(-thrA, -thrA), nB = pack2(-thrB, -thrB);
   const unsigned char *base = reinterpret_cast<const unsigned char *>(pf);
   uint32_t ae = 0, ao = 0, be = 0, bo = 0;
+#ifndef FAST_PF_UNROLL
+#define FAST_PF_UNROLL 8   // slots per loop trip (measured: 4 -> 8 -1 %, 16 no further gain)
+#endif
 #pragma unroll 1
-  for (int k = 0; k < 32; k += 4) {
+  for (int k = 0; k < 32; k += FAST_PF_UNROLL) {
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < FAST_PF_UNROLL; u++) {
       const ulonglong2 p = *reinterpret_cast<const ulonglong2 *>(base + (k + u) * STRIDE);
       const uint64_t dx = f2_sub(p.x, xf2), dy = f2_sub(p.y, yf2);
       const uint64_t tA = f2_fma(dx, dx, f2_fma(dy, dy, nA));
@@ -477,76 +480,82 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
   // the last quarter of the launch: 24 of 28 warps per SM on average).
   for (int64_t k = blockIdx.x, k_next = 0; k < env_count; k = k_next) {
     const int64_t e = env_begin + k;
+    sf_mbar_wait(bar, parity);  // the inputs of this environment have landed
+    parity ^= 1;
+
+    // Phase 0 is split into arithmetic (registers only, reads the input arrays) and stores: everything phase 0 writes
+    // is also a source of the previous environment's bulk stores, and the ~300 instructions of arithmetic hide the
+    // time the copy engine takes to read them out of shared memory (the wait sat at the loop top until round 2:
+    // every thread of the CTA idled there behind the elected thread).
+    // ---- phase 0a: target t (src/agent/target.py:27-60) ----
+    double t_x = S.tx[t], t_y = S.ty[t], t_h = S.th[t];
+    float t_vx, t_vy;
+    {
+      double sh, ch;
+      heading_sincos(t_h, P.sincos_tab, sh, ch);
+      t_x += P.dtv_t * ch;
+      t_y += P.dtv_t * sh;
+      // reflection (target.py:52-58); cos(-h) = cos h, sin(-h) = -sin h, cos(+-pi - h) = -cos h, sin(+-pi - h) = sin h
+      if (0 > t_y || t_y > P.y_max) { t_h = -t_h; sh = -sh; }
+      else if (t_x < 0 || t_x > P.x_max) { t_h = (t_h > 0) ? (PI_D - t_h) : (-PI_D - t_h); ch = -ch; }
+      t_vx = (float)ch * P.tv_over_uv_f; t_vy = (float)sh * P.tv_over_uv_f;
+    }
+    const float txf = (float)(t_x - P.cx), tyf = (float)(t_y - P.cy);
+    float rabs = fmaxf(fabsf(txf), fabsf(tyf));
+    // ---- phase 0b: UAV t (src/agent/uav.py:73-99) ----
+    double xi, yi, hi;      // state after the move
+    float xf, yf, chf, shf, xl, yl;  // own fp32 position relative to the centre, heading, and what fp32 dropped of the position
+    const double xo_d = S.ux[t], yo_d = S.uy[t];
+    const int a_old = S.ua[t], ai = S.act[t];
+    float xof, yof, cof, sof;
+    {
+      double h = S.uh[t];
+      double sh, ch;
+      heading_sincos(h, P.sincos_tab, sh, ch);
+      cof = (float)ch; sof = (float)sh;
+      xof = (float)(xo_d - P.cx); yof = (float)(yo_d - P.cy);
+      xi = xo_d + P.dtv_u * ch;
+      yi = yo_d + P.dtv_u * sh;
+      double dh;
+      float cd, sd;
+      if ((unsigned)ai < (unsigned)P.na) {
+        const ActEntry en = act_tab[ai];
+        dh = en.dth; cd = en.cd; sd = en.sd;
+      } else {  // the reference's formula accepts any integer (uav.py:73-81)
+        dh = P.dt * ((double)(2 * (ai + 1) - P.na - 1) * P.uav_h_max / (double)(P.na - 1));
+        double sd_, cd_;
+        sincos_shared(dh, &sd_, &cd_);
+        cd = (float)cd_; sd = (float)sd_;
+      }
+      hi = wrap_heading(h + dh);
+      // cos / sin of the new heading by angle addition in fp32: they only feed the observation (the next step
+      // evaluates the stored heading again)
+      chf = fmaf(cof, cd, -(sof * sd));
+      shf = fmaf(sof, cd, cof * sd);
+      xf = (float)(xi - P.cx); yf = (float)(yi - P.cy);
+      xl = (float)((xi - P.cx) - (double)xf); yl = (float)((yi - P.cy) - (double)yf);
+      rabs = fmaxf(fmaxf(rabs, fmaxf(fabsf(xf), fabsf(yf))), fmaxf(fabsf(xof), fabsf(yof)));
+      // fp32 sums of action indices are exact only for small integers: anything else takes the exact path
+      if ((unsigned)ai >= 4096u || (unsigned)a_old >= 4096u) rabs = __int_as_float(0x7f800000);
+      if (!(rabs == rabs)) rabs = __int_as_float(0x7f800000);
+    }
     // The thread that committed the previous outputs waits until they have left shared memory.  (Bulk groups belong
     // to the issuing thread: elect.sync with a full mask picks the same lane every time.)
     if (warp == 0) {
       if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     __syncthreads();
-    sf_mbar_wait(bar, parity);
-    parity ^= 1;
-
-    // ---- phase 0a: target t (src/agent/target.py:27-60) ----
-    float rabs;
     {
-      double x = S.tx[t], y = S.ty[t], h = S.th[t];
-      double sh, ch;
-      heading_sincos(h, P.sincos_tab, sh, ch);
-      x += P.dtv_t * ch;
-      y += P.dtv_t * sh;
-      // reflection (target.py:52-58); cos(-h) = cos h, sin(-h) = -sin h, cos(+-pi - h) = -cos h, sin(+-pi - h) = sin h
-      if (0 > y || y > P.y_max) { h = -h; sh = -sh; }
-      else if (x < 0 || x > P.x_max) { h = (h > 0) ? (PI_D - h) : (-PI_D - h); ch = -ch; }
-      S.otx[t] = x; S.oty[t] = y; S.oth[t] = h;
-      const float txf = (float)(x - P.cx), tyf = (float)(y - P.cy);
+      S.otx[t] = t_x; S.oty[t] = t_y; S.oth[t] = t_h;
       float *ts = reinterpret_cast<float *>(&S.tslot[ih]) + ic;
-      ts[0] = txf; ts[2] = tyf;
-      ts[4] = (float)ch * P.tv_over_uv_f; ts[6] = (float)sh * P.tv_over_uv_f;
-      rabs = fmaxf(fabsf(txf), fabsf(tyf));
+      ts[0] = txf; ts[2] = tyf; ts[4] = t_vx; ts[6] = t_vy;
       if (AUX) S.tcnt[t] = 0;
-    }
-    // ---- phase 0b: UAV t (src/agent/uav.py:73-99) ----
-    double xi, yi;
-    float xf, yf, chf, shf, xl, yl;  // own fp32 position relative to the centre, heading, and what fp32 dropped of the position
-    int ai;
-    {
-      double x = S.ux[t], y = S.uy[t], h = S.uh[t];
-      const int a_old = S.ua[t], act = S.act[t];
-      double sh, ch;
-      heading_sincos(h, P.sincos_tab, sh, ch);
-      const float cof = (float)ch, sof = (float)sh;
-      const float xof = (float)(x - P.cx), yof = (float)(y - P.cy);
-      S.xo[t] = x; S.yo[t] = y;
+      S.xo[t] = xo_d; S.yo[t] = yo_d;
       float *so = reinterpret_cast<float *>(&S.sloto[ih]) + ic;
       so[0] = xof; so[2] = yof; so[4] = cof; so[6] = sof; so[8] = (float)a_old;
-      x += P.dtv_u * ch;
-      y += P.dtv_u * sh;
-      double dh;
-      float cd, sd;
-      if ((unsigned)act < (unsigned)P.na) {
-        const ActEntry en = act_tab[act];
-        dh = en.dth; cd = en.cd; sd = en.sd;
-      } else {  // the reference's formula accepts any integer (uav.py:73-81)
-        dh = P.dt * ((double)(2 * (act + 1) - P.na - 1) * P.uav_h_max / (double)(P.na - 1));
-        double sd_, cd_;
-        sincos_shared(dh, &sd_, &cd_);
-        cd = (float)cd_; sd = (float)sd_;
-      }
-      h = wrap_heading(h + dh);
-      // cos / sin of the new heading by angle addition in fp32: they only feed the observation (the next step
-      // evaluates the stored heading again)
-      chf = fmaf(cof, cd, -(sof * sd));
-      shf = fmaf(sof, cd, cof * sd);
-      xf = (float)(x - P.cx); yf = (float)(y - P.cy);
-      xl = (float)((x - P.cx) - (double)xf); yl = (float)((y - P.cy) - (double)yf);
-      S.oux[t] = x; S.ouy[t] = y; S.ouh[t] = h; S.oua[t] = act;
+      S.oux[t] = xi; S.ouy[t] = yi; S.ouh[t] = hi; S.oua[t] = ai;
       float *sn = reinterpret_cast<float *>(&S.slotn[ih]) + ic;
-      sn[0] = xf; sn[2] = yf; sn[4] = chf; sn[6] = shf; sn[8] = (float)act;
-      rabs = fmaxf(fmaxf(rabs, fmaxf(fabsf(xf), fabsf(yf))), fmaxf(fabsf(xof), fabsf(yof)));
-      // fp32 sums of action indices are exact only for small integers: anything else takes the exact path
-      if ((unsigned)act >= 4096u || (unsigned)a_old >= 4096u) rabs = __int_as_float(0x7f800000);
-      if (!(rabs == rabs)) rabs = __int_as_float(0x7f800000);
-      xi = x; yi = y; ai = act;
+      sn[0] = xf; sn[2] = yf; sn[4] = chf; sn[6] = shf; sn[8] = (float)ai;
     }
     {
       const uint32_t rm = __reduce_max_sync(0xffffffffu, __float_as_uint(rabs));
@@ -645,6 +654,7 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
       uint32_t ccE, ccO, d0_, d1_;
       prefilter64<false, (int)sizeof(SlotRec)>(S.slotn, xf, yf, Tf_hi, 0.f, ccE, ccO, d0_, d1_);
       const unsigned char *slot_new = reinterpret_cast<const unsigned char *>(S.slotn);
+      const unsigned char *slot_old = reinterpret_cast<const unsigned char *>(S.sloto);
       // -- ONE walk over the candidate slots, two partners per trip, for the three UAV-UAV lists:
       //    communication (uav.py:124-147; the partner's record after its move if it moved first, before it otherwise),
       //    duplicate-tracking punishment (uav.py:214-229) and the neighbour set (uav.py:305), both at NEW positions.
@@ -664,16 +674,20 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
           w ^= bit;
           const unsigned char *rn = slot_new + 48 * b;
           const bool moved = b < ihx;
-          const unsigned char *rp = rn + (moved ? 0u : OLD_OFF);
+          const unsigned char *rp = (moved ? slot_new : slot_old) + 48 * b;  // (one select and one multiply-add)
           const ulonglong2 hd = *reinterpret_cast<const ulonglong2 *>(rp + 16);   // {cos0, cos1}, {sin0, sin1}
           const uint64_t aa = *reinterpret_cast<const uint64_t *>(rp + 32);       // {a0, a1}
           const ulonglong2 pn = *reinterpret_cast<const ulonglong2 *>(rn);        // positions after the move
           // position before the move = position after it - dt v (cos h, sin h) of the OLD heading (uav.py:88-94): two
           // packed FMAs instead of a third 16-byte load per trip; the communication guard carries the extra rounding
+#ifndef FAST_DIRECT_OLD
           const float mv = moved ? 0.0f : ndtv_f;
           const uint64_t mv2 = pack2(mv, mv);
           ulonglong2 p;
           p.x = f2_fma(hd.x, mv2, pn.x); p.y = f2_fma(hd.y, mv2, pn.y);
+#else   // A/B switch: the stored old position (a fourth load per trip)
+          const ulonglong2 p = *reinterpret_cast<const ulonglong2 *>(rp);
+#endif
           const uint64_t dx = f2_sub(p.x, xf2), dy = f2_sub(p.y, yf2);
           const uint64_t s2 = f2_fma(dx, dx, f2_mul(dy, dy));
           const float s0 = f2_lo(s2), s1 = f2_hi(s2);
