@@ -664,61 +664,23 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
       //    communication trips; here it rides on the communication trips for +20 instructions each.)
       {
         uint64_t sx = 0, sy = 0, sc = 0, ss = 0, sa = 0, cn = 0, dp2 = 0;
-        float smax_c = 0.f, smax_d = 0.f, smax_n = 0.f;
+        float smax_c = 0.f, smax_d = 0.f, dmin_n = 3.0e38f;
+        const float Tp_nx = __uint_as_float(__float_as_uint(Tp_hi) + 1u);   // the float above Tp_hi (positive)
+        const uint64_t tpn2 = pack2(Tp_nx, Tp_nx);
+        // |n - T| <= T - Tp_lo covers Tp_lo <= n <= Tp_hi (and as much above T); never narrower than a few ulp of T
+        const float nb_band = fmaxf(__fadd_ru(Tp_nx, -Tp_lo), 4.0f * (Tp_nx - Tp_hi));
         const uint64_t kx1 = pack2(k_ex1, k_ex1), kx0 = pack2(k_ex0, k_ex0);
         uint32_t w = ccE | ccO;
-#pragma unroll 1
-        while (w) {
-          const int b = sf_msb(w);
-          const uint32_t bit = 1u << b;
-          w ^= bit;
-          const unsigned char *rn = slot_new + 48 * b;
-          const bool moved = b < ihx;
-          const unsigned char *rp = (moved ? slot_new : slot_old) + 48 * b;  // (one select and one multiply-add)
-          const ulonglong2 hd = *reinterpret_cast<const ulonglong2 *>(rp + 16);   // {cos0, cos1}, {sin0, sin1}
-          const uint64_t aa = *reinterpret_cast<const uint64_t *>(rp + 32);       // {a0, a1}
-          const ulonglong2 pn = *reinterpret_cast<const ulonglong2 *>(rn);        // positions after the move
-          // position before the move = position after it - dt v (cos h, sin h) of the OLD heading (uav.py:88-94): two
-          // packed FMAs instead of a third 16-byte load per trip; the communication guard carries the extra rounding
-#ifndef FAST_DIRECT_OLD
-          const float mv = moved ? 0.0f : ndtv_f;
-          const uint64_t mv2 = pack2(mv, mv);
-          ulonglong2 p;
-          p.x = f2_fma(hd.x, mv2, pn.x); p.y = f2_fma(hd.y, mv2, pn.y);
-#else   // A/B switch: the stored old position (a fourth load per trip)
-          const ulonglong2 p = *reinterpret_cast<const ulonglong2 *>(rp);
-#endif
-          const uint64_t dx = f2_sub(p.x, xf2), dy = f2_sub(p.y, yf2);
-          const uint64_t s2 = f2_fma(dx, dx, f2_mul(dy, dy));
-          const float s0 = f2_lo(s2), s1 = f2_hi(s2);
-          const bool h0 = s0 <= Tc_hi, h1 = s1 <= Tc_hi;
-          const uint64_t wh = pack2(h0 ? 1.0f : 0.0f, h1 ? 1.0f : 0.0f);
-          {  // largest accepted squared distance through the weights: one packed product and one three-way maximum
-            const uint64_t sw = f2_mul(s2, wh);
-            smax_c = fmaxf(fmaxf(smax_c, f2_lo(sw)), f2_hi(sw));
-          }
-          sx = f2_fma(wh, dx, sx); sy = f2_fma(wh, dy, sy);
-          sc = f2_fma(wh, hd.x, sc); ss = f2_fma(wh, hd.y, ss);
-          sa = f2_fma(wh, aa, sa);
-          cn = f2_add(cn, wh);
-          if (AUX) { if (h0) cmE |= bit; if (h1) cmO |= bit; }
-          // duplicate tracking / neighbours at the new positions
-          const uint64_t ex = f2_sub(pn.x, xf2), ey = f2_sub(pn.y, yf2);
-          const uint64_t n2 = f2_fma(ex, ex, f2_mul(ey, ey));
-          const float n0 = f2_lo(n2), n1 = f2_hi(n2);
-          const bool g0 = n0 <= T2_hi, g1 = n1 <= T2_hi;
-          const uint64_t wg = pack2(g0 ? 1.0f : 0.0f, g1 ? 1.0f : 0.0f);
-          {
-            const uint64_t nw = f2_mul(n2, wg);
-            smax_d = fmaxf(fmaxf(smax_d, f2_lo(nw)), f2_hi(nw));
-          }
           const uint64_t arg = f2_fma(pack2(fast_sqrtf(n0), fast_sqrtf(n1)), kx1, kx0);
           dp2 = f2_fma(wg, pack2(fast_ex2f(f2_lo(arg)), fast_ex2f(f2_hi(arg))), dp2);  // exp((2dp - d)/(2dp))
           if (AUX) { if (g0) dpE |= bit; if (g1) dpO |= bit; }
-          {  // neighbour bits and their largest accepted squared distance through all-ones / zero masks
-            const uint32_t m0 = (n0 <= Tp_hi) ? 0xffffffffu : 0u, m1 = (n1 <= Tp_hi) ? 0xffffffffu : 0u;
+          {  // Neighbour bits from the SIGN of n - T (T = the float above Tp_hi: n <= Tp_hi iff n - T < 0), spread over the
+             // word by an arithmetic shift; the smallest |n - T| seen tells afterwards whether any partner sat in the
+             // band around the radius (either side of it: a few more checked walks, never a wrong bit).
+            const uint64_t dn = f2_sub(n2, tpn2);
+            const uint32_t m0 = (uint32_t)((int32_t)(uint32_t)dn >> 31), m1 = (uint32_t)((int32_t)(uint32_t)(dn >> 32) >> 31);
             nbE |= m0 & bit; nbO |= m1 & bit;
-            smax_n = fmaxf(fmaxf(smax_n, __uint_as_float(__float_as_uint(n0) & m0)), __uint_as_float(__float_as_uint(n1) & m1));
+            dmin_n = fminf(fminf(dmin_n, fabsf(f2_lo(dn))), fabsf(f2_hi(dn)));
           }
         }
         // own entry of the own slot: the record that was read there (new if this UAV sits in the odd place, else old)
@@ -729,7 +691,7 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
           const float *r = reinterpret_cast<const float *>(slot_new + (ic ? 0u : OLD_OFF) + 48 * ih) + ic;
           own_c = r[4]; own_s = r[6]; own_a = r[8];
           // the same arithmetic as the walk: 0 in the odd place (new record), one move back in the even place
-          own_dx = fmaf(own_c, ic ? 0.0f : ndtv_f, xf) - xf; own_dy = fmaf(own_s, ic ? 0.0f : ndtv_f, yf) - yf;
+          own_dx = own_c * (ic ? 0.0f : ndtv_f); own_dy = own_s * (ic ? 0.0f : ndtv_f);  // fma(c, mv, xf - xf)
           const float s_own = fmaf(own_dx, own_dx, own_dy * own_dy);
           own_w = sf_le(s_own, Tc_hi);
         }
@@ -758,7 +720,7 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
         float dup = (f2_lo(dp2) + f2_hi(dp2)) - fast_ex2f(fmaf(fast_sqrtf(0.f), k_ex1, k_ex0));
         nbE &= ~ownE; nbO &= ~ownO;
         if (AUX) { dpE &= ~ownE; dpO &= ~ownO; }
-        if ((smax_d > T2_lo) || (smax_n > Tp_lo)) {  // a pair inside a guard band: this list once more, checked
+        if ((smax_d > T2_lo) || (dmin_n <= nb_band)) {  // a pair inside a guard band: this list once more, checked
           DupOut X;
           sf_dup_checked<N, M, AUX>(&S, WO, T2_lo, T2_hi, Tp_lo, Tp_hi, P.s_2dp_le, P.s_dp_le, k_ex0, k_ex1, (ccE | ccO) & ~ownE,
                                     (ccE | ccO) & ~ownO, &X);
