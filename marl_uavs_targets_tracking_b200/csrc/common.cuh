@@ -174,8 +174,14 @@ __device__ __forceinline__ int warp_max(int v) {
 
 // Block-wide reduction of per-thread statistics into this CTA's slot (accumulating across launches;
 // one writer per slot, no atomics, so the totals are reproducible for a fixed launch geometry).
-// the four reward sums of the fast step kernel as 64-bit fixed-point counts (exact, order-independent)
-__device__ inline void block_stats_commit_fx(long long *red /*smem [2][4]*/, long long *slot, long long v0, long long v1, long long v2,
+// Statistics of kernels whose CTAs draw their work from a launch-wide counter (KParams::fast_ctr): which CTA steps
+// which environment depends on timing, so the reward sums are kept as integer counts of 2^-22 -- exact, hence the same
+// totals whatever the grouping.  A value in [-1, 1] as such a count: v + 3 lies in [2, 4], where consecutive floats are
+// 2^-22 apart and the bit pattern is linear in the value (round to nearest even): FADD + IADD3.
+__device__ __forceinline__ int sf_fx(float v) { return __float_as_int(v + 3.0f) - 0x40400000; }
+
+// the four reward sums as 64-bit fixed-point counts
+__device__ inline void block_stats_commit_fx(long long *red /*smem [warps][4]*/, long long *slot, long long v0, long long v1, long long v2,
                                              long long v3) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int o = 16; o > 0; o >>= 1) {
@@ -183,9 +189,14 @@ __device__ inline void block_stats_commit_fx(long long *red /*smem [2][4]*/, lon
     v2 += __shfl_xor_sync(0xffffffffu, v2, o); v3 += __shfl_xor_sync(0xffffffffu, v3, o);
   }
   __syncthreads();
-  if (lane == 0 && wid < 2) { red[wid * 4 + 0] = v0; red[wid * 4 + 1] = v1; red[wid * 4 + 2] = v2; red[wid * 4 + 3] = v3; }
+  const int nw = (int)(blockDim.x >> 5);   // (red holds [nw][4], nw <= 9)
+  if (lane == 0) { red[wid * 4 + 0] = v0; red[wid * 4 + 1] = v1; red[wid * 4 + 2] = v2; red[wid * 4 + 3] = v3; }
   __syncthreads();
-  if (threadIdx.x < 4) slot[threadIdx.x] += red[threadIdx.x] + red[4 + threadIdx.x];
+  if (threadIdx.x < 4) {
+    long long a = 0;
+    for (int w = 0; w < nw; w++) a += red[w * 4 + threadIdx.x];
+    slot[threadIdx.x] += a;
+  }
   __syncthreads();
 }
 

@@ -150,9 +150,6 @@ __device__ __forceinline__ int sf_msb(uint32_t w) {  // index of the highest set
   asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(w));
   return r;
 }
-// A value in [-1, 1] as a count of 2^-22: v + 3 lies in [2, 4], where consecutive floats are 2^-22 apart and the bit
-// pattern is linear in the value (round to nearest even).  FADD + IADD3 instead of a conversion and an fp64 add.
-__device__ __forceinline__ int sf_fx(float v) { return __float_as_int(v + 3.0f) - 0x40400000; }
 __device__ __forceinline__ float sf_rcp(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -671,6 +668,47 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
         const float nb_band = fmaxf(__fadd_ru(Tp_nx, -Tp_lo), 4.0f * (Tp_nx - Tp_hi));
         const uint64_t kx1 = pack2(k_ex1, k_ex1), kx0 = pack2(k_ex0, k_ex0);
         uint32_t w = ccE | ccO;
+#pragma unroll 1
+        while (w) {
+          const int b = sf_msb(w);
+          const uint32_t bit = 1u << b;
+          w ^= bit;
+          const unsigned char *rn = slot_new + 48 * b;
+          const bool moved = b < ihx;
+          const unsigned char *rp = (moved ? slot_new : slot_old) + 48 * b;  // (one select and one multiply-add)
+          const ulonglong2 hd = *reinterpret_cast<const ulonglong2 *>(rp + 16);   // {cos0, cos1}, {sin0, sin1}
+          const uint64_t aa = *reinterpret_cast<const uint64_t *>(rp + 32);       // {a0, a1}
+          const ulonglong2 pn = *reinterpret_cast<const ulonglong2 *>(rn);        // positions after the move
+          // offsets at the new positions (duplicate tracking / neighbours), and from them the offsets the communication
+          // test needs: the partner's position BEFORE its move is the one after it minus dt v (cos h, sin h) of the OLD
+          // heading (uav.py:88-94), so one packed FMA per axis replaces a third 16-byte load and a subtraction; the
+          // communication guard carries the extra rounding
+          const uint64_t ex = f2_sub(pn.x, xf2), ey = f2_sub(pn.y, yf2);
+          const float mv = moved ? 0.0f : ndtv_f;
+          const uint64_t mv2 = pack2(mv, mv);
+          const uint64_t dx = f2_fma(hd.x, mv2, ex), dy = f2_fma(hd.y, mv2, ey);
+          const uint64_t s2 = f2_fma(dx, dx, f2_mul(dy, dy));
+          const float s0 = f2_lo(s2), s1 = f2_hi(s2);
+          const bool h0 = s0 <= Tc_hi, h1 = s1 <= Tc_hi;
+          const uint64_t wh = pack2(h0 ? 1.0f : 0.0f, h1 ? 1.0f : 0.0f);
+          {  // largest accepted squared distance through the weights: one packed product and one three-way maximum
+            const uint64_t sw = f2_mul(s2, wh);
+            smax_c = fmaxf(fmaxf(smax_c, f2_lo(sw)), f2_hi(sw));
+          }
+          sx = f2_fma(wh, dx, sx); sy = f2_fma(wh, dy, sy);
+          sc = f2_fma(wh, hd.x, sc); ss = f2_fma(wh, hd.y, ss);
+          sa = f2_fma(wh, aa, sa);
+          cn = f2_add(cn, wh);
+          if (AUX) { if (h0) cmE |= bit; if (h1) cmO |= bit; }
+          // duplicate tracking / neighbours at the new positions
+          const uint64_t n2 = f2_fma(ex, ex, f2_mul(ey, ey));
+          const float n0 = f2_lo(n2), n1 = f2_hi(n2);
+          const bool g0 = n0 <= T2_hi, g1 = n1 <= T2_hi;
+          const uint64_t wg = pack2(g0 ? 1.0f : 0.0f, g1 ? 1.0f : 0.0f);
+          {
+            const uint64_t nw = f2_mul(n2, wg);
+            smax_d = fmaxf(fmaxf(smax_d, f2_lo(nw)), f2_hi(nw));
+          }
           const uint64_t arg = f2_fma(pack2(fast_sqrtf(n0), fast_sqrtf(n1)), kx1, kx0);
           dp2 = f2_fma(wg, pack2(fast_ex2f(f2_lo(arg)), fast_ex2f(f2_hi(arg))), dp2);  // exp((2dp - d)/(2dp))
           if (AUX) { if (g0) dpE |= bit; if (g1) dpO |= bit; }

@@ -500,19 +500,34 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
 
   const int64_t ngroups = (env_count + epb - 1) / epb;
   // per-thread statistics, reduced once at the end (src/train.py:181-192)
-  double st_r = 0, st_tt = 0, st_bp = 0, st_dup = 0, st_cov = 0, st_envs = 0;
+  // (reward sums as fixed-point counts: the groups beyond the first wave come from a launch-wide counter, common.cuh)
+  long long fx_r = 0, fx_tt = 0, fx_bp = 0, fx_dup = 0;
+  double st_cov = 0, st_envs = 0;
   int st_cmax = 0;
+  long long *const s_next = reinterpret_cast<long long *>(S.red + 63);  // (the reduction buffer is idle inside the loop)
 
-  for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+  // Groups beyond the first wave are handed out by a launch-wide counter, as in the fast kernel: the warp schedulers
+  // favour some CTAs, and with a fixed stride the favoured ones retire early and leave their SM under-occupied.
+  long long drawn = 0;
+  if (tid == 0 && (int64_t)blockIdx.x < ngroups) drawn = (long long)gridDim.x + (long long)atomicAdd(P.fast_ctr, 1);
+  for (int64_t grp = blockIdx.x, grp_next = 0; grp < ngroups; grp = grp_next) {
     const int64_t e0 = env_begin + grp * epb;
     const int ne = (int)min((int64_t)epb, env_begin + env_count - e0);
     if (tid < epb) { S.far[tid] = 0; S.cov[tid] = 0; }  // (their readers of the previous iteration have passed a barrier)
+    if (tid == 0) *s_next = drawn;
+    __syncthreads();                // previous iteration's readers are done; dth table visible
+    grp_next = *s_next;
+#ifdef GENERIC_STATIC_STRIDE   // A/B switch: the fixed stride of round 1
+    grp_next = grp + gridDim.x;
+#endif
+    // (thread 0 draws one group ahead: the atomic's round trip is over by the time the next iteration asks for it)
+    if (tid == 0 && grp_next < ngroups) drawn = (long long)gridDim.x + (long long)atomicAdd(P.fast_ctr, 1);
     if (!WARP_ENV) {
       // Small-swarm instances are bound by global-load latency, not by issue slots (10x10: long-scoreboard stalls
       // dominate): pull the state of this CTA's NEXT group of environments into L2 while this one is computed, one
       // prefetch per 128-byte line.  (The 64x64 instance is issue-bound; there the extra instructions cost more than
       // the latency they hide.)
-      const int64_t grp_n = grp + gridDim.x;
+      const int64_t grp_n = grp_next;
       if (grp_n < ngroups) {
         const int64_t e0n = env_begin + grp_n * epb;
         const int nen = (int)min((int64_t)epb, env_begin + env_count - e0n);  // the last group may be partial: stay inside the arrays
@@ -522,7 +537,6 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
         for (int q = tid * 16; q < nen * m; q += NT * 16) { pf(B.tx + e0n * m + q); pf(B.ty + e0n * m + q); pf(B.th + e0n * m + q); }
       }
     }
-    __syncthreads();                // previous iteration's readers are done; dth table visible
 
     // ---- phase 0a: targets (src/agent/target.py:27-60) ----
     for (int q = tid; q < ne * m; q += NT) {
@@ -643,11 +657,11 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
         B.nbr_bits[gi * 2 + 1] = (uint64_t)O.nb[2] | ((uint64_t)O.nb[3] << 32);
       }
       r = fmin(fmax(r, -1.0), 1.0);  // clip_and_normalize(reward, -1, 1) is a plain clip
-      if (!pmi_pending) { B.rew4[gi] = (float)r; st_r += r; }
+      if (!pmi_pending) { B.rew4[gi] = (float)r; fx_r += sf_fx((float)r); }
       B.rew4[plane + gi] = (float)ttn;
       B.rew4[2 * plane + gi] = (float)bpn;
       B.rew4[3 * plane + gi] = (float)dupn;
-      st_tt += ttn; st_bp += bpn; st_dup += dupn;
+      fx_tt += sf_fx((float)ttn); fx_bp += sf_fx((float)bpn); fx_dup += sf_fx((float)dupn);
     }
     // environment.py:246-253: targets with at least one UAV strictly within dp, counted cooperatively
     for (int k = tid; k < ne * m; k += NT) {
@@ -670,6 +684,11 @@ uavsim_step_kernel(const KParams P, const UavSimBuffers B, const double *__restr
       st_envs += 1.0;
     }
   }
-  block_stats_commit(S.red, stats_partial + (size_t)blockIdx.x * STAT_W, st_r, st_tt, st_bp, st_dup, st_cov, st_cmax,
-                     st_envs, NT);
+  if (tid == 0) {  // the last CTA to leave rewinds the counter for the next launch
+    __threadfence();
+    if (atomicAdd(P.fast_ctr + 1, 1) == (int)gridDim.x - 1) { P.fast_ctr[0] = 0; P.fast_ctr[1] = 0; __threadfence(); }
+  }
+  block_stats_commit_fx(reinterpret_cast<long long *>(S.red), reinterpret_cast<long long *>(stats_partial + 2 * (size_t)P.stat_slots * STAT_W) + (size_t)blockIdx.x * STAT_W,
+                        fx_r, fx_tt, fx_bp, fx_dup);
+  block_stats_commit(S.red, stats_partial + (size_t)blockIdx.x * STAT_W, 0.0, 0.0, 0.0, 0.0, st_cov, st_cmax, st_envs, NT);
 }
