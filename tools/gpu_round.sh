@@ -16,3 +16,5 @@ ncu --set full --clock-control none --import-source on -k regex:uavsim_step_tile
 ncu --set full --clock-control none --import-source on -k regex:uavsim_step_small -s 10 -c 1 -o gpurun_out/prof_r2_small -f python bench.py --workload default4096 --no-extras --steps 20 --warmup 5 --e2e-steps 2 > gpurun_out/r2_ncu_d.log 2>&1
 UAVSIM_LIB=variants/libuavsim_nopairs.so ncu --set full --clock-control none -k regex:uavsim_step_fast -s 10 -c 1 -o gpurun_out/prof_r2_fast_nopairs -f python bench.py --steps 20 --warmup 5 --no-extras --e2e-steps 2 > gpurun_out/r2_ncu_e.log 2>&1
 tail -3 gpurun_out/r2_gputests.log
+python tools/generic_timing.py > gpurun_out/r2_generic_timing.log 2>&1
+python tools/pmi_hidden_timing.py > gpurun_out/r2_pmi_hidden_timing.log 2>&1
