@@ -490,14 +490,25 @@ static int pmi_tc_launch(uavsim_t *h, int64_t e0, int64_t cnt, double coop, cuda
   PmiTcDev W;
   W.w0 = h->pmi.w0; W.b0 = h->pmi.b0; W.b1 = h->pmi.b1; W.w2 = h->pmi.w2; W.b2 = h->pmi.b2;
   W.w1_tiles = h->d_tc_tiles;
-  const int64_t ngroups = (cnt + h->tc_g - 1) / h->tc_g;
+  // Group size: the largest that fits (tc_g) fixes the number of waves over the one-CTA-per-SM grid; within that number
+  // of waves the groups are made equal, so that every CTA gets the same count (16 384 environments of 10 UAVs: 51 per
+  // group would be 322 groups = 2.2 per CTA, i.e. three for some and two for most; 37 per group is 443 = three for all).
+  int G = h->tc_g;
+  {
+    const int64_t g_max = (cnt + G - 1) / G;
+    const int64_t waves = (g_max + h->sm_count - 1) / h->sm_count;
+    const int64_t slots = waves * h->sm_count;
+    const int64_t g_even = (cnt + slots - 1) / slots;
+    if (g_even >= 1 && g_even < G) G = (int)g_even;
+  }
+  const int64_t ngroups = (cnt + G - 1) / G;
   int grid = (int)(ngroups < h->sm_count ? ngroups : h->sm_count);
   if (grid > h->stat_slots) grid = h->stat_slots;
   if (h->pmi.H == 64)
-    uavsim_pmi_tc_kernel<64><<<grid, TC_NT, TcSmem::total, st>>>(h->kp, h->buf, W, e0, cnt, h->tc_g, coop,
+    uavsim_pmi_tc_kernel<64><<<grid, TC_NT, TcSmem::total, st>>>(h->kp, h->buf, W, e0, cnt, G, coop,
                                                                 h->d_stats + (size_t)h->stat_slots * STAT_W);
   else
-    uavsim_pmi_tc_kernel<128><<<grid, TC_NT, TcSmem::total, st>>>(h->kp, h->buf, W, e0, cnt, h->tc_g, coop,
+    uavsim_pmi_tc_kernel<128><<<grid, TC_NT, TcSmem::total, st>>>(h->kp, h->buf, W, e0, cnt, G, coop,
                                                                  h->d_stats + (size_t)h->stat_slots * STAT_W);
   CUDA_TRY(cudaGetLastError());
   h->launches++;
