@@ -641,15 +641,19 @@ static bool fast_path_usable(const uavsim_t *h) {
 // Automatic choice for small swarms: the two-warp kernel while the batch fits ~2.5 waves of its CTAs (there the step is
 // bound by the dependency chain of a thread, which that kernel halves), the generic kernel beyond (throughput-bound: one
 // thread per UAV issues ~13 % fewer warp instructions; measured at 65 536 environments of 10 x 10: 0.072 vs 0.082 ms).
-static bool small_path_in_use(const uavsim_t *h, int64_t cnt) {
+// In the rollout loop below the FFI (`rollout`: the policy is drawn inside this kernel and the launches overlap through
+// programmatic dependent launch, one launch per step instead of two) it stays ahead up to ~10 waves (10 x 10, device loop,
+// tools/generic_timing.py: 16 384 envs 0.026 vs 0.042 ms, 49 152 envs 0.065 vs 0.068, 65 536 envs 0.086 vs 0.079).
+static bool small_path_in_use(const uavsim_t *h, int64_t cnt, bool rollout = false) {
   if (!h->has_small || (h->step_path != 0 && h->step_path != 4)) return false;
   if (h->step_path == 4) return true;
   const int G = small_group(h->kp.n, h->kp.m);
-  return (cnt + G - 1) / G <= (int64_t)h->small_grid_max[0] * 5 / 2;
+  const int64_t waves2 = rollout ? 20 : 5;  // twice the number of waves
+  return (cnt + G - 1) / G <= (int64_t)h->small_grid_max[0] * waves2 / 2;
 }
 static int launch_step_range(uavsim_t *h, int mode, double coop, int64_t e0, int64_t cnt, int done_flag, cudaStream_t st,
                              int rng_on = 0, uint64_t rng_seed = 0, uint32_t rng_step = 0) {
-  if (small_path_in_use(h, cnt)) {  // groups of environments in two-warp CTAs
+  if (small_path_in_use(h, cnt, rng_on != 0)) {  // groups of environments in two-warp CTAs
     const int v = (h->buf.obs_mask || h->buf.tracker_cnt) ? 1 : 0;
     const int G = small_group(h->kp.n, h->kp.m);
     const int64_t groups = (cnt + G - 1) / G;
@@ -717,7 +721,7 @@ extern "C" int uavsim_run_random_policy(uavsim_t *h, int mode, double coop, uint
   if (rc) return rc;
   if (nsteps < 0) { SET_ERR("uavsim_run_random_policy: nsteps < 0"); return UAVSIM_ERR_ARG; }
   for (int64_t k = 0; k < nsteps; k++) {
-    if (small_path_in_use(h, h->E)) {  // the draw happens inside the step kernel: one launch per step
+    if (small_path_in_use(h, h->E, true)) {  // the draw happens inside the step kernel: one launch per step
       CUDA_TRY(cudaSetDevice(h->device));
       h->t++;
       const int done = (h->hp.num_steps > 0 && h->t >= h->hp.num_steps) ? 1 : 0;
