@@ -137,6 +137,18 @@ int uavsim_run_random_policy(uavsim_t *h, int mode, double cooperative, uint64_t
 int uavsim_step_host(uavsim_t *h, int mode, double cooperative, const int32_t *h_actions, float *h_obs,
                      float *h_rew4, int32_t *h_covered, int chunks, void *stream);
 
+/* The same step queued without waiting: returns once the copies and kernels are enqueued and hands back a ticket;
+ * uavsim_step_host_wait(ticket) blocks until that step's outputs are in its host buffers.  A caller that already
+ * holds the next actions (a random or scripted policy, an action sequence under evaluation) may queue step t+1 --
+ * with OTHER host output buffers -- before waiting for step t: the download of step t then overlaps the upload and
+ * the kernels of step t+1 (chunk by chunk; the library orders the device-side reuse of the action and output
+ * arrays itself).  At most two steps should be in flight; every other entry point of the handle must only be
+ * called after the last ticket has been waited for.  (src/train.py:142-196 is closed-loop -- the next action
+ * depends on this observation -- and uses uavsim_step_host.) */
+int uavsim_step_host_async(uavsim_t *h, int mode, double cooperative, const int32_t *h_actions, float *h_obs,
+                           float *h_rew4, int32_t *h_covered, int chunks, void *stream, int64_t *ticket);
+int uavsim_step_host_wait(uavsim_t *h, int64_t ticket);
+
 /* alpha/beta/gamma are re-read from config on every Environment.step (src/environment.py:219-220);
  * this updates them without recreating the handle. */
 int uavsim_set_reward_weights(uavsim_t *h, double alpha, double beta, double gamma);

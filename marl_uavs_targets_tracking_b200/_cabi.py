@@ -58,6 +58,9 @@ SYMBOLS = {
     "uavsim_run_random_policy": (C.c_int, [_H, C.c_int, C.c_double, C.c_uint64, C.c_int64, C.c_int64, C.c_void_p]),
     "uavsim_step_host": (C.c_int, [_H, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_int, C.c_void_p]),
+    "uavsim_step_host_async": (C.c_int, [_H, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_int, C.c_void_p, C.POINTER(C.c_int64)]),
+    "uavsim_step_host_wait": (C.c_int, [_H, C.c_int64]),
     "uavsim_set_reward_weights": (C.c_int, [_H, C.c_double, C.c_double, C.c_double]),
     "uavsim_set_pmi_weights": (C.c_int, [_H, C.POINTER(UavSimPmiWeights), C.c_void_p]),
     "uavsim_set_pmi_path": (C.c_int, [_H, C.c_int]),

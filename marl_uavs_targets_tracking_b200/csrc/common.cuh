@@ -134,7 +134,9 @@ struct uavsim {
   size_t smem_pmi;
   // host-buffer pipeline
   cudaStream_t s_in, s_comp, s_out;
-  cudaEvent_t ev_user, ev_in[16], ev_comp[16];
+  cudaEvent_t ev_user, ev_in[16], ev_comp[16], ev_out[16], ev_done[2];
+  int host_chunks;            // chunk count of the host-buffer steps queued so far (0: none yet)
+  int64_t host_steps_queued;  // tickets issued by uavsim_step_host / _async
   int64_t t, launches;
 };
 

@@ -323,7 +323,9 @@ static int uavsim_create_impl(const UavSimParams *p, int64_t n_envs, int64_t env
   for (int c = 0; c < 16; c++) {
     CUDA_TRY(cudaEventCreateWithFlags(&h->ev_in[c], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&h->ev_comp[c], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_out[c], cudaEventDisableTiming));
   }
+  for (int c = 0; c < 2; c++) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_done[c], cudaEventDisableTiming));
   *out = h;
   return 0;
 }
@@ -340,7 +342,9 @@ extern "C" int uavsim_destroy(uavsim_t *h) {
   for (int c = 0; c < 16; c++) {
     if (h->ev_in[c]) cudaEventDestroy(h->ev_in[c]);
     if (h->ev_comp[c]) cudaEventDestroy(h->ev_comp[c]);
+    if (h->ev_out[c]) cudaEventDestroy(h->ev_out[c]);
   }
+  for (int c = 0; c < 2; c++) if (h->ev_done[c]) cudaEventDestroy(h->ev_done[c]);
   free(h);
   return 0;
 }
@@ -737,15 +741,25 @@ extern "C" int uavsim_run_random_policy(uavsim_t *h, int mode, double coop, uint
   return 0;
 }
 
-extern "C" int uavsim_step_host(uavsim_t *h, int mode, double coop, const int32_t *h_actions, float *h_obs,
-                                float *h_rew4, int32_t *h_covered, int chunks, void *stream) {
-  int rc = check_step_args(h, mode, coop, "uavsim_step_host");
+// Queues one host-buffer step over `chunks` environment ranges on the three internal streams and returns without
+// waiting.  Per chunk: actions up (s_in) -> step kernel (s_comp) -> outputs down (s_out).  Across consecutive calls the
+// same chunk of the NEXT step is ordered behind this one's by events: its upload behind this kernel (the kernel reads
+// the action array), its kernel behind this download (the kernel overwrites the output arrays), so the download of
+// step t -- the link is the bottleneck: 268.7 MB at 64 x 64 x 65 536 -- overlaps upload and kernels of step t+1.
+static int step_host_queue(uavsim_t *h, int mode, double coop, const int32_t *h_actions, float *h_obs, float *h_rew4,
+                           int32_t *h_covered, int chunks, void *stream, const char *who) {
+  int rc = check_step_args(h, mode, coop, who);
   if (rc) return rc;
-  if (!h_actions) { SET_ERR("uavsim_step_host: h_actions is NULL"); return UAVSIM_ERR_ARG; }
+  if (!h_actions) { SET_ERR("%s: h_actions is NULL", who); return UAVSIM_ERR_ARG; }
   CUDA_TRY(cudaSetDevice(h->device));
   if (chunks < 1) chunks = 1;
   if (chunks > 16) chunks = 16;
   if ((int64_t)chunks > h->E) chunks = (int)h->E;
+  if (h->host_chunks && h->host_chunks != chunks) {  // other chunk boundaries: the per-chunk events no longer line up
+    CUDA_TRY(cudaStreamSynchronize(h->s_out));
+    CUDA_TRY(cudaStreamSynchronize(h->s_comp));
+  }
+  h->host_chunks = chunks;
   const int n = h->kp.n;
   const int64_t E = h->E;
   h->t++;
@@ -757,9 +771,11 @@ extern "C" int uavsim_step_host(uavsim_t *h, int mode, double coop, const int32_
   CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_user, 0));
   for (int c = 0; c < chunks; c++) {
     const int64_t e0 = E * c / chunks, e1 = E * (c + 1) / chunks, cnt = e1 - e0;
+    if (h->host_steps_queued) CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_comp[c], 0));   // previous kernel has read its actions
     CUDA_TRY(cudaMemcpyAsync(h->buf.actions + e0 * n, h_actions + e0 * n, sizeof(int32_t) * cnt * n, cudaMemcpyHostToDevice, h->s_in));
     CUDA_TRY(cudaEventRecord(h->ev_in[c], h->s_in));
     CUDA_TRY(cudaStreamWaitEvent(h->s_comp, h->ev_in[c], 0));
+    if (h->host_steps_queued) CUDA_TRY(cudaStreamWaitEvent(h->s_comp, h->ev_out[c], 0));  // previous outputs have left the device
     rc = launch_step_range(h, mode, coop, e0, cnt, done, h->s_comp);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(h->ev_comp[c], h->s_comp));
@@ -771,9 +787,36 @@ extern "C" int uavsim_step_host(uavsim_t *h, int mode, double coop, const int32_
         CUDA_TRY(cudaMemcpyAsync(h_rew4 + (k * E + e0) * n, h->buf.rew4 + (k * E + e0) * n, sizeof(float) * cnt * n, cudaMemcpyDeviceToHost, h->s_out));
     if (h_covered)
       CUDA_TRY(cudaMemcpyAsync(h_covered + e0, h->buf.covered + e0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, h->s_out));
+    CUDA_TRY(cudaEventRecord(h->ev_out[c], h->s_out));
   }
+  CUDA_TRY(cudaEventRecord(h->ev_done[h->host_steps_queued & 1], h->s_out));
+  h->host_steps_queued++;
+  return 0;
+}
+
+extern "C" int uavsim_step_host(uavsim_t *h, int mode, double coop, const int32_t *h_actions, float *h_obs,
+                                float *h_rew4, int32_t *h_covered, int chunks, void *stream) {
+  const int rc = step_host_queue(h, mode, coop, h_actions, h_obs, h_rew4, h_covered, chunks, stream, "uavsim_step_host");
+  if (rc) return rc;
   CUDA_TRY(cudaStreamSynchronize(h->s_out));
   CUDA_TRY(cudaStreamSynchronize(h->s_comp));
+  return 0;
+}
+
+extern "C" int uavsim_step_host_async(uavsim_t *h, int mode, double coop, const int32_t *h_actions, float *h_obs,
+                                      float *h_rew4, int32_t *h_covered, int chunks, void *stream, int64_t *ticket) {
+  const int rc = step_host_queue(h, mode, coop, h_actions, h_obs, h_rew4, h_covered, chunks, stream, "uavsim_step_host_async");
+  if (rc) return rc;
+  if (ticket) *ticket = h->host_steps_queued - 1;
+  return 0;
+}
+
+extern "C" int uavsim_step_host_wait(uavsim_t *h, int64_t ticket) {
+  if (!h) { SET_ERR("uavsim_step_host_wait: NULL handle"); return UAVSIM_ERR_ARG; }
+  if (ticket < 0 || ticket >= h->host_steps_queued) { SET_ERR("uavsim_step_host_wait: ticket %lld was never issued", (long long)ticket); return UAVSIM_ERR_ARG; }
+  CUDA_TRY(cudaSetDevice(h->device));
+  // (two event slots: if later steps reused this one, the wait covers them too -- the streams run in order)
+  CUDA_TRY(cudaEventSynchronize(h->ev_done[ticket & 1]));
   return 0;
 }
 

@@ -314,6 +314,28 @@ class BatchedEnvironment:
                                                    ptr(h_covered), int(chunks), self._stream()), "uavsim_step_host")
         self._host = None
 
+    def step_host_async(self, config, pmi, h_actions, h_obs=None, h_rew4=None, h_covered=None, chunks=4):
+        """uavsim_step_host_async: the same step queued without waiting; returns a ticket for step_host_wait.  Queue
+        step t+1 (other host output buffers) before waiting for step t and the download of step t overlaps the upload
+        and the kernels of step t+1.  Wait for the last ticket before any other call on this environment."""
+        if self._h is None:
+            raise UavSimError("step before reset")
+        self._sync_weights(config)
+        mode, coop = self._mode(config, pmi)
+        ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
+        ticket = C.c_int64(-1)
+        with self._on_device():
+            _cabi.check(self._lib.uavsim_step_host_async(self._h, mode, coop, ptr(h_actions), ptr(h_obs), ptr(h_rew4),
+                                                         ptr(h_covered), int(chunks), self._stream(), C.byref(ticket)),
+                        "uavsim_step_host_async")
+        self._host = None
+        return int(ticket.value)
+
+    def step_host_wait(self, ticket):
+        """Blocks until the outputs of the step with this ticket are in its host buffers."""
+        with self._on_device():
+            _cabi.check(self._lib.uavsim_step_host_wait(self._h, int(ticket)), "uavsim_step_host_wait")
+
     @property
     def actions(self):
         """The bound int32 [E,n] action buffer the next step_device(config, pmi) call reads."""

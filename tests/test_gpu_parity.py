@@ -425,6 +425,40 @@ def test_sharding_is_invisible_in_the_results():
         e.close()
 
 
+def test_queued_host_buffer_steps_equal_device_steps():
+    """uavsim_step_host_async / _wait: step t+1 is queued (other host buffers) before the outputs of step t are read;
+    every step's outputs must equal the device-resident run's, for changing chunk counts too (64x64: the fast kernel,
+    whose launch-wide counter must be back at zero between the chunk launches)."""
+    from marl_uavs_targets_tracking_b200 import default_config
+    n = m = 64
+    cfg = default_config("MAAC-G", n, m)
+    E, T = 3000, 9
+    a_env, b_env = _env(n, m, cfg, E, seed=12), _env(n, m, cfg, E, seed=12)
+    a_env.reset(cfg); b_env.reset(cfg)
+    acts, want = [], []
+    for t in range(T):
+        acts.append(a_env.random_actions(6, t).cpu().pin_memory())
+        o, r, c = a_env.step_device(cfg, None)
+        want.append((o.cpu(), r.cpu(), c.cpu()))
+    bufs = [(torch.empty((E, n, 12), dtype=torch.float32).pin_memory(), torch.empty((4, E, n), dtype=torch.float32).pin_memory(),
+             torch.empty((E,), dtype=torch.int32).pin_memory()) for _ in range(2)]
+    chunks = lambda t: 4 if t < 6 else 7  # noqa: E731
+    tk = b_env.step_host_async(cfg, None, acts[0], *bufs[0], chunks=chunks(0))
+    for t in range(1, T):
+        tk2 = b_env.step_host_async(cfg, None, acts[t], *bufs[t & 1], chunks=chunks(t))
+        b_env.step_host_wait(tk)
+        got = bufs[(t - 1) & 1]
+        assert torch.equal(got[0], want[t - 1][0]) and torch.equal(got[1], want[t - 1][1]) and torch.equal(got[2], want[t - 1][2]), t
+        tk = tk2
+    b_env.step_host_wait(tk)
+    got = bufs[(T - 1) & 1]
+    assert torch.equal(got[0], want[T - 1][0]) and torch.equal(got[1], want[T - 1][1]) and torch.equal(got[2], want[T - 1][2])
+    sa, sb = a_env.get_state(), b_env.get_state()
+    assert all(torch.equal(sa[k], sb[k]) for k in sa)
+    assert a_env.episode_stats() == b_env.episode_stats()
+    a_env.close(); b_env.close()
+
+
 @pytest.mark.parametrize("method,hidden", [("MAAC-G", 0), ("MAAC-R", 64), ("MAAC-R", 128)])
 def test_host_buffer_step_equals_device_step(method, hidden):
     """uavsim_step_host pipelines env ranges over streams; hidden = 64 takes the CUDA-core PMI kernel, 128 the tensor
