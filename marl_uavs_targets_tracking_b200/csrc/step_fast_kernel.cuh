@@ -411,6 +411,9 @@ __device__ __noinline__ void sf_dup_checked(const FastSmem<N, M, AUX> *Sp, const
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
+#ifndef FAST_LOAD_WARP
+#define FAST_LOAD_WARP 1   // the warp whose elected thread draws the next environment and issues its bulk loads
+#endif
 #ifndef FAST_CTAS_PER_SM
 #define FAST_CTAS_PER_SM 14
 #endif
@@ -559,7 +562,7 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
       if (lane == 0) S.rmax[warp] = rm;
     }
     __syncthreads();
-    if (warp == 0) {  // next environment, behind the pair phase
+    if (warp == FAST_LOAD_WARP) {  // next environment, behind the pair phase (warp 0 issues the twelve stores: the duties are split)
       if (elect_one()) {
         const int64_t kn = (int64_t)gridDim.x + (int64_t)atomicAdd(P.fast_ctr, 1);
         S.next_k = kn;
