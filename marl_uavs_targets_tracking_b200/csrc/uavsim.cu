@@ -782,9 +782,9 @@ static int step_host_queue(uavsim_t *h, int mode, double coop, const int32_t *h_
     CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_comp[c], 0));
     if (h_obs)
       CUDA_TRY(cudaMemcpyAsync(h_obs + e0 * n * 12, h->buf.obs + e0 * n * 12, sizeof(float) * cnt * n * 12, cudaMemcpyDeviceToHost, h->s_out));
-    if (h_rew4)
-      for (int k = 0; k < 4; k++)
-        CUDA_TRY(cudaMemcpyAsync(h_rew4 + (k * E + e0) * n, h->buf.rew4 + (k * E + e0) * n, sizeof(float) * cnt * n, cudaMemcpyDeviceToHost, h->s_out));
+    if (h_rew4)  // the chunk's rows of the four reward planes [4][E][n]: one strided copy (pitch = one plane)
+      CUDA_TRY(cudaMemcpy2DAsync(h_rew4 + e0 * n, sizeof(float) * E * n, h->buf.rew4 + e0 * n, sizeof(float) * E * n,
+                                 sizeof(float) * cnt * n, 4, cudaMemcpyDeviceToHost, h->s_out));
     if (h_covered)
       CUDA_TRY(cudaMemcpyAsync(h_covered + e0, h->buf.covered + e0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, h->s_out));
     CUDA_TRY(cudaEventRecord(h->ev_out[c], h->s_out));
