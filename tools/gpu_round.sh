@@ -17,4 +17,6 @@ ncu --set full --clock-control none --import-source on -k regex:uavsim_step_smal
 UAVSIM_LIB=variants/libuavsim_nopairs.so ncu --set full --clock-control none -k regex:uavsim_step_fast -s 10 -c 1 -o gpurun_out/prof_r2_fast_nopairs -f python bench.py --steps 20 --warmup 5 --no-extras --e2e-steps 2 > gpurun_out/r2_ncu_e.log 2>&1
 tail -3 gpurun_out/r2_gputests.log
 python tools/generic_timing.py > gpurun_out/r2_generic_timing.log 2>&1
-python tools/pmi_hidden_timing.py > gpurun_out/r2_pmi_hidden_timing.log 2>&1
+PYTHONPATH=. python tools/pmi_hidden_timing.py > gpurun_out/r2_pmi_hidden_timing.log 2>&1
+python tools/pmi_small_timing.py > gpurun_out/r2_pmi_small_timing.log 2>&1
+python tools/e2e_timing.py > gpurun_out/r2_e2e_timing.log 2>&1
