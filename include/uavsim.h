@@ -171,7 +171,9 @@ int uavsim_set_pmi_path(uavsim_t *h, int path);
 /* Episode statistics accumulated by uavsim_step since the last reset (src/train.py:181-192):
  * out[0..3] = sums of rewards / tracking / boundary / duplicate over env-steps and UAVs,
  * out[4] = sum of covered_targets over env-steps, out[5] = max covered_targets,
- * out[6] = env-steps accumulated, out[7] = 0.  Synchronises `stream`. */
+ * out[6] = env-steps accumulated, out[7] = 0.  Synchronises `stream`.  The reward sums of the step kernels are
+ * accumulated as integer counts of 2^-22 per (environment, UAV, step) -- exact in any order, so the totals are
+ * bit-reproducible although CTAs draw their environments from a counter; resolution 2.4e-7 per value. */
 int uavsim_episode_stats(uavsim_t *h, double out[8], void *stream);
 
 /* number of kernels this handle has launched (bench.py reports it as gpu_launches) */

@@ -342,7 +342,7 @@ def test_long_episode_64x64_does_not_stall():
 def test_headline_batch_sampled_against_the_oracle(oracle):
     """BASELINE.json configs[3] at full size (64x64, 65 536 environments): 96 environments spread over the batch are
     replayed in the CPU oracle for a whole 200-step episode -- covered / tracker counts bit-exact every step, state,
-    observation and rewards within tolerance -- so the full-size launch geometry (persistent grid, grid-stride over
+    observation and rewards within tolerance -- so the full-size launch geometry (persistent grid, counter-scheduled walk over
     environments, last partial wave) is checked against the reference semantics, not only against itself."""
     from marl_uavs_targets_tracking_b200 import default_config
     n = m = 64
