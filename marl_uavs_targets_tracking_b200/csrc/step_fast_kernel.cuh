@@ -414,6 +414,9 @@ __device__ __noinline__ void sf_dup_checked(const FastSmem<N, M, AUX> *Sp, const
 #ifndef FAST_LOAD_WARP
 #define FAST_LOAD_WARP 1   // the warp whose elected thread draws the next environment and issues its bulk loads
 #endif
+#ifndef FAST_COV_THREAD
+#define FAST_COV_THREAD 32  // the thread that writes the covered count / done flag of an environment (warp 1: warp 0 issues the stores)
+#endif
 #ifndef FAST_CTAS_PER_SM
 #define FAST_CTAS_PER_SM 14
 #endif
@@ -604,6 +607,7 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
       const uint64_t xf2 = pack2(xf, xf), yf2 = pack2(yf, yf);
       const WalkOwn WO = {xi, yi, xf, yf, t};
 
+      uint32_t ccE, ccO;  // UAV candidate slots (even / odd partner)
       // -- targets: observe_target (uav.py:101-122), tracking reward (uav.py:199-212), coverage (environment.py:246-253)
       {
         uint32_t d0, d1;
@@ -651,7 +655,7 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
       //    position, at most dt*v from the new one) or the duplicate-tracking radius 2 dp, whichever is larger
       //    (KParams::g_pf).  The own bit is always set (distance 0): the own slot is walked like any other and the own
       //    contributions, known in closed form, are taken out afterwards.
-      uint32_t ccE, ccO, d0_, d1_;
+      uint32_t d0_, d1_;
       prefilter64<false, (int)sizeof(SlotRec)>(S.slotn, xf, yf, Tf_hi, 0.f, ccE, ccO, d0_, d1_);
       const unsigned char *slot_new = reinterpret_cast<const unsigned char *>(S.slotn);
       const unsigned char *slot_old = reinterpret_cast<const unsigned char *>(S.sloto);
@@ -838,10 +842,18 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
         // uav.py:293-310 -- the conditional expression covers the whole sum: no neighbour -> 0
         float s = 0;
         const int cnt = __popc(nbE) + __popc(nbO);
-#pragma unroll
-        for (int par = 0; par < 2; par++) {
-          uint32_t w = par ? nbO : nbE;
-          while (w) { const int b = sf_msb(w); w ^= 1u << b; s += S.raw[2 * b + par]; }
+        {  // one trip per slot with a neighbour: both raw rewards of the slot in one 8-byte load
+          uint32_t u = nbE | nbO;
+          float s1 = 0;
+          while (u) {
+            const int b = sf_msb(u);
+            const uint32_t bit = 1u << b;
+            u ^= bit;
+            const float2 rr = *reinterpret_cast<const float2 *>(&S.raw[2 * b]);
+            s += (nbE & bit) ? rr.x : 0.0f;
+            s1 += (nbO & bit) ? rr.y : 0.0f;
+          }
+          s += s1;
         }
         const float cf = (float)coop;
         r = cnt ? fmaf(1.0f - cf, raw, cf * s * sf_rcp((float)cnt)) : 0.0f;
@@ -883,7 +895,7 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
-    if (t == 0) {
+    if (t == FAST_COV_THREAD) {
       const int c = __popc(S.cover[0][0] | S.cover[1][0]) + __popc(S.cover[0][1] | S.cover[1][1]);
       B.covered[e] = c;
       if (B.done) B.done[e] = done_flag;
