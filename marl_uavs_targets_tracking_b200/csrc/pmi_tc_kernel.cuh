@@ -293,13 +293,23 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
   static_assert(NCHUNK % (2 * TC_NS) == 0, "ring schedule assumes an even number of ring turns per set");
   uint32_t t = 0;   // sets processed so far by this CTA (phase of the accumulator barriers); same sequence in all roles
   const int64_t ngroups = (env_count + G - 1) / G;
-  double st_r = 0;
+  // Groups beyond the first per CTA come from the launch-wide counter (KParams::fast_ctr, rewound by the last CTA to
+  // leave): the pair count of a group follows the swarm's density, so equal group COUNTS are not equal work.  Thread 0
+  // draws one group ahead; every role reads the index behind the barrier at the loop top.  The reward sum is a
+  // fixed-point count for the same reason as in the step kernels (common.cuh: sf_fx).
+  long long fx_r = 0;
+  long long *const s_next = reinterpret_cast<long long *>(smem + TcSmem::bar + 112);  // (mbarriers end at +112 at most, the tensor-memory pointer sits at +120)
+  long long drawn = 0;
+  if (tid == 0 && (int64_t)blockIdx.x < ngroups) drawn = (long long)gridDim.x + (long long)atomicAdd(P.fast_ctr, 1);
 
-  for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+  for (int64_t grp = blockIdx.x, grp_next = 0; grp < ngroups; grp = grp_next) {
     const int64_t e0 = env_begin + grp * G;
     const int ne = (int)min((int64_t)G, env_begin + env_count - e0);
     const int A = ne * n;  // UAVs in this group (<= TC_AMAX)
+    if (tid == 0) *s_next = drawn;
     __syncthreads();
+    grp_next = *s_next;
+    if (tid == 0 && grp_next < ngroups) drawn = (long long)gridDim.x + (long long)atomicAdd(P.fast_ctr, 1);
     for (int k = tid; k < A * 12; k += TC_NT) s_obs[k] = B.obs[e0 * n * 12 + k];
     for (int a = tid; a < A; a += TC_NT) {
       s_raw[a] = B.raw[e0 * n + a];
@@ -567,11 +577,17 @@ uavsim_pmi_tc_kernel(const KParams P, const UavSimBuffers B, const PmiTcDev W, i
         }
         r = fmin(fmax(r, -1.0), 1.0);
         B.rew4[e0 * n + a] = (float)r;
-        st_r += r;
+        fx_r += sf_fx((float)r);
       }
     }
   }
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512u) : "memory");
-  block_stats_commit(s_red, stats_partial + (size_t)blockIdx.x * STAT_W, st_r, 0, 0, 0, 0, 0, 0, TC_NT);
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(P.fast_ctr + 1, 1) == (int)gridDim.x - 1) { P.fast_ctr[0] = 0; P.fast_ctr[1] = 0; __threadfence(); }
+  }
+  // (stats_partial is the PMI region of the statistics array; the fixed-point region follows it)
+  block_stats_commit_fx(reinterpret_cast<long long *>(s_red),
+                        reinterpret_cast<long long *>(stats_partial + (size_t)P.stat_slots * STAT_W) + (size_t)blockIdx.x * STAT_W, fx_r, 0, 0, 0);
 }
