@@ -404,6 +404,8 @@ def measure_workload(torch, dist, env_cls, args, name, rank, world, device, step
         try:
             h_obs2, h_rew2, h_cov2 = torch.empty_like(h_obs).pin_memory(), torch.empty_like(h_rew).pin_memory(), torch.empty_like(h_cov).pin_memory()
             outs = ((h_obs, h_rew, h_cov), (h_obs2, h_rew2, h_cov2))
+            for i in range(2):  # both buffer sets and the other chunk count once before the clock starts
+                env.step_host_wait(env.step_host_async(cfg, pmi, h_act[i % NH], *outs[i & 1], chunks=2))
             barrier()
             t0 = time.perf_counter()
             acc = 0.0

@@ -20,3 +20,4 @@ python tools/generic_timing.py > gpurun_out/r2_generic_timing.log 2>&1
 PYTHONPATH=. python tools/pmi_hidden_timing.py > gpurun_out/r2_pmi_hidden_timing.log 2>&1
 python tools/pmi_small_timing.py > gpurun_out/r2_pmi_small_timing.log 2>&1
 python tools/e2e_timing.py > gpurun_out/r2_e2e_timing.log 2>&1
+ncu --set full --clock-control none -k regex:pmi_tc -s 3 -c 1 -o gpurun_out/prof_r2_pmi_tc -f python bench.py --workload swarm64_pmi --steps 8 --warmup 3 --no-extras --e2e-steps 2 > gpurun_out/r2_ncu_pmi.log 2>&1

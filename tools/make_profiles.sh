@@ -9,6 +9,9 @@ python tools/ncu_summary.py $G/prof_r2_fast_s100.ncu-rep > $P/r2_step_fast_kerne
 python tools/ncu_summary.py $G/prof_r2_fast_nopairs.ncu-rep > $P/r2_step_fast_kernel_nopairs_ncu.txt
 python tools/ncu_summary.py $G/prof_r2_tile_dense.ncu-rep > $P/r2_step_tile_kernel_ncu.txt
 python tools/ncu_summary.py $G/prof_r2_small.ncu-rep > $P/r2_step_small_kernel_ncu.txt
+python tools/ncu_summary.py $G/prof_r2_pmi_tc.ncu-rep > $P/r2_pmi_tc_kernel_ncu.txt
+cp $P/r2_step_fast_kernel_ncu.txt $P/r2_step_kernel_ncu.txt   # the name VERDICT r1 asked for: the default 64x64 step kernel
+for f in r2_generic_timing r2_pmi_hidden_timing r2_pmi_small_timing r2_e2e_timing; do cp $G/$f.log $P/$f.txt; done
 python tools/ncu_segments.py $G/prof_r2_fast_dense.ncu-rep uavsim_step_fast_kernelILi64ELi64ELb0 --warps 2 --min-share 0.3 > $P/r2_step_fast_kernel_segments.txt
 python tools/ncu_segments.py $G/prof_r2_tile_dense.ncu-rep uavsim_step_tile_kernelILb0 --warps 4 --min-share 0.3 > $P/r2_step_tile_kernel_segments.txt
 python tools/ncu_segments.py $G/prof_r2_small.ncu-rep uavsim_step_small_kernelILb0 --envs 1366 --warps 2 --min-share 0.5 > $P/r2_step_small_kernel_segments.txt
