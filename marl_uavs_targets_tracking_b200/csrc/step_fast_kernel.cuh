@@ -2,6 +2,10 @@
 // src/environment.py:120-164), one environment per 64-thread CTA, persistent over environments.
 //
 // What differs from the generic kernel (step_kernel.cuh), and why:
+//   * Work distribution.  Every resident CTA starts on the environment of its block index and draws each further one
+//     from a launch-wide counter (KParams::fast_ctr; the last CTA to leave rewinds it).  With a fixed stride the warp
+//     schedulers' preference for some CTAs let those finish early and the SMs ran at 24 of 28 resident warps; the
+//     counter was worth 10 %.  The reward statistics are therefore integer sums (sf_fx): order-independent.
 //   * Data movement.  The eight state / action arrays of an environment (3.5 KB) arrive by cp.async.bulk (TMA engine,
 //     mbarrier complete_tx) while the previous environment is computed, and the outputs (new state, observations,
 //     four reward planes: 7.4 KB) leave by bulk shared -> global copies; no thread issues a global load or store
@@ -17,10 +21,10 @@
 //     lists, fp64 sums and all -- which took 13 % of the issued instructions.)
 //     The observation sums are fp32 (outputs are fp32, contract 1e-5; measured ~2e-7).
 //   * Candidate walks.  A sign-bit prefilter (packed f32x2 FMAs, as in the generic kernel) marks the partners inside
-//     each guarded radius; three short walks consume them: targets (observation + tracking reward + coverage),
-//     communication partners (new record if the partner moved first, old record otherwise: src/agent/uav.py:124-147
-//     in the update order of src/environment.py:133-138), and duplicate-tracking / neighbour partners
-//     (src/agent/uav.py:214-229, :305).  UAV records are stored two per SLOT (partners 2b and 2b+1 side by side in
+//     each guarded radius; two walks consume them: targets (observation + tracking reward + coverage), and ONE walk
+//     over the UAV slots for communication partners (new record if the partner moved first, old record otherwise:
+//     src/agent/uav.py:124-147 in the update order of src/environment.py:133-138), duplicate-tracking and neighbour
+//     partners (src/agent/uav.py:214-229, :305).  UAV records are stored two per SLOT (partners 2b and 2b+1 side by side in
 //     the halves of the packed fp32 registers): the UAV walks visit slots, not partners, and evaluate both partners
 //     of a slot with f32x2 arithmetic and 0/1 weights -- a swarm that flies in formation has its partners in runs of
 //     consecutive indices, so the trips nearly halve exactly when the candidate lists are long.
@@ -662,10 +666,11 @@ uavsim_step_fast_kernel(const KParams P, const UavSimBuffers B, const ActEntry *
       // -- ONE walk over the candidate slots, two partners per trip, for the three UAV-UAV lists:
       //    communication (uav.py:124-147; the partner's record after its move if it moved first, before it otherwise),
       //    duplicate-tracking punishment (uav.py:214-229) and the neighbour set (uav.py:305), both at NEW positions.
-      //    Weights 1 / 0 from the upper guards; per list the largest accepted squared distance tells afterwards
-      //    whether an accepted pair sat inside the band.  (Until round 2 the duplicate / neighbour list had its own
-      //    prefilter radius and its own walk, one partner per trip: 27 trips of 22 instructions on top of the 20
-      //    communication trips; here it rides on the communication trips for +20 instructions each.)
+      //    Weights 1 / 0 from the upper guards; per list one running extreme (largest accepted squared distance, or the
+      //    smallest |n - T| for the neighbour bits) tells afterwards whether a pair sat inside the band.  (Until round 2
+      //    the duplicate / neighbour list had its own prefilter radius and its own walk, one partner per trip: 27 trips
+      //    of 22 instructions on top of the 20 communication trips; here it rides on the communication trips.  The trip
+      //    is 52 instructions with two 16-byte loads and one 8-byte load: tools/loop_count.py.)
       {
         uint64_t sx = 0, sy = 0, sc = 0, ss = 0, sa = 0, cn = 0, dp2 = 0;
         float smax_c = 0.f, smax_d = 0.f, dmin_n = 3.0e38f;
