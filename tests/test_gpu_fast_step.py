@@ -331,3 +331,31 @@ def test_counter_scheduled_launch_is_reproducible_and_complete():
     assert a[4]["covered_sum"] == g[4]["covered_sum"] and a[4]["covered_max"] == g[4]["covered_max"]
     for k in ("rewards", "target_tracking_reward", "boundary_punishment", "duplicate_tracking_punishment"):
         assert abs(a[4][k] - g[4][k]) <= 1e-6 * max(1.0, abs(g[4][k])), k
+
+
+def test_rollout_loop_and_stepwise_route_agree_between_the_kernel_ranges():
+    """Between ~2.5 and ~10 waves of the small-swarm kernel's CTAs the rollout loop below the FFI (policy drawn inside the
+    small-swarm kernel) and the step-by-step route (random_actions + step: generic kernel) run DIFFERENT kernels on the
+    same Philox draws: every integer output and the state's last actions must be identical, floats within 2e-6."""
+    from marl_uavs_targets_tracking_b200 import default_config
+    n = m = 10
+    cfg = default_config("MAAC-G", n, m)
+    E, T = 20000, 15
+    a, b = _env(n, m, cfg, E, seed=41), _env(n, m, cfg, E, seed=41)
+    a.reset(cfg); b.reset(cfg)
+    for t in range(T):
+        a.random_actions(13, t)
+        oa, ra, ca = a.step_device(cfg, None)
+    ob, rb, cb = b.run_random_policy(cfg, None, 13, 0, T)
+    assert torch.equal(ca, cb)
+    sa, sb = a.get_state(), b.get_state()
+    assert torch.equal(sa["ua"], sb["ua"])
+    for k in ("ux", "uy", "uh", "tx", "ty", "th"):
+        assert max_scaled_err(sa[k].cpu().numpy(), sb[k].cpu().numpy()) <= 1e-9, k
+    assert max_scaled_err(oa.double().cpu().numpy(), ob.double().cpu().numpy()) <= TOL_TIGHT
+    assert max_scaled_err(ra.double().cpu().numpy(), rb.double().cpu().numpy()) <= TOL_TIGHT
+    x, y = a.episode_stats(), b.episode_stats()
+    assert x["covered_sum"] == y["covered_sum"] and x["covered_max"] == y["covered_max"] and x["env_steps"] == y["env_steps"] == E * T
+    for k in ("rewards", "target_tracking_reward", "boundary_punishment", "duplicate_tracking_punishment"):
+        assert abs(x[k] - y[k]) <= 1e-6 * max(1.0, abs(x[k])), k
+    a.close(); b.close()
