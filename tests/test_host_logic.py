@@ -178,3 +178,19 @@ def test_actor_critic_checkpoints_have_the_reference_layout(tmp_path):
         assert torch.equal(v, w), k
     for (k, v), (_, w) in zip(a.critic.state_dict().items(), b.critic.state_dict().items()):
         assert torch.equal(v, w), k
+
+
+def test_fixed_point_statistic_trick_is_linear_on_the_reward_range():
+    """common.cuh: sf_fx(v) = bits(float32(v + 3)) - bits(3.0f) is the reward v in [-1, 1] as a count of 2^-22, rounded
+    to nearest even -- the step kernels accumulate these integers so that the episode statistics do not depend on
+    which CTA stepped which environment.  Restated in numpy: linear, exact at the ends, error <= 2^-23 per value, and
+    integer sums are order-independent where float sums are not."""
+    rng = np.random.RandomState(5)
+    v = np.concatenate([rng.uniform(-1, 1, 200000), [-1.0, 1.0, 0.0, -0.0, 2.0 ** -30, -2.0 ** -30, 0.5, -0.5]]).astype(np.float32)
+    fx = (v + np.float32(3.0)).astype(np.float32).view(np.int32).astype(np.int64) - 0x40400000
+    assert fx[-8] == -(1 << 22) and fx[-7] == (1 << 22) and fx[-6] == 0 and fx[-5] == 0
+    assert np.array_equal(fx, np.rint(v.astype(np.float64) * (1 << 22)).astype(np.int64))
+    assert np.max(np.abs(fx / float(1 << 22) - v.astype(np.float64))) <= 2.0 ** -23
+    perm = rng.permutation(v.size)
+    assert fx.sum() == fx[perm].sum()
+    assert abs(fx.sum() / float(1 << 22) - v.astype(np.float64).sum()) <= 1e-9 * v.size
