@@ -68,7 +68,9 @@ struct KParams {
   float dtv_u_f;  // dt*v_max of the UAVs in fp32
   const double *sincos_tab;  // [FM_TAB_SIZE][2] sine / cosine of k pi/32 (fast_math.cuh), device memory
   int stat_slots;            // slots per region of the statistics array
-  int *fast_ctr;             // fast step kernel: {next environment beyond the first wave, CTAs that have left}, zero between launches
+  int *fast_ctr;             // counter-scheduled kernels (fast / generic step, PMI tensor): {next unit of work beyond the first
+                             // wave, CTAs that have left}; zero between launches (the last CTA to leave rewinds it); launches of one
+                             // handle are stream-ordered, so one pair serves all of them
 };
 
 struct PmiDev {
@@ -119,7 +121,7 @@ struct uavsim {
   int tile_grid_max[2];
   ActEntry *d_act;          // [na] per action: dt * rate (fp64), cos / sin of it (fp32)
   double *d_sctab;          // sine / cosine table of the fast kernel's heading routine
-  int *d_fast_ctr;          // work counter of the fast kernel (KParams::fast_ctr)
+  int *d_fast_ctr;          // work counter of the counter-scheduled kernels (KParams::fast_ctr)
   // pmi
   bool has_pmi;
   PmiDev pmi;
@@ -191,7 +193,7 @@ __device__ inline void block_stats_commit_fx(long long *red /*smem [warps][4]*/,
     v2 += __shfl_xor_sync(0xffffffffu, v2, o); v3 += __shfl_xor_sync(0xffffffffu, v3, o);
   }
   __syncthreads();
-  const int nw = (int)(blockDim.x >> 5);   // (red holds [nw][4], nw <= 9)
+  const int nw = (int)(blockDim.x >> 5);   // (red holds [nw][4]: the callers' 64-entry buffers serve up to 16 warps)
   if (lane == 0) { red[wid * 4 + 0] = v0; red[wid * 4 + 1] = v1; red[wid * 4 + 2] = v2; red[wid * 4 + 3] = v3; }
   __syncthreads();
   if (threadIdx.x < 4) {
